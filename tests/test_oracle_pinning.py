@@ -1,0 +1,173 @@
+"""Pin the oracle (oracle/) on outputs of the unmodified reference.
+
+The reference has no tests / golden vectors; the fixtures in
+tests/golden/ were produced by tests/golden/make_golden.py, which runs the
+reference's own compiled kernel and Python layers.  When oracle/_ref is present
+the C restatement is additionally compared with the live reference kernel.
+"""
+import numpy as np
+import pytest
+from scipy import sparse
+
+CASES = [("sqrt", 1e-10), ("sqrt", 1.0), ("log10", 1.0), ("log10", 0.5), ("linear", 0.0)]
+
+
+def _d(z, name, psc):
+    if name == "sqrt":
+        return np.sqrt(np.abs(z) + psc) * np.sign(z)
+    if name == "log10":
+        return np.log10(np.abs(z) + psc) * np.sign(z)
+    return z
+
+
+def _degenerate_pairs(e):
+    C = e.shape[1]
+    return np.array([[np.array_equal(e[:, i], e[:, c]) for i in range(C)] for c in range(C)])
+
+
+@pytest.mark.parametrize("name,psc", CASES)
+def test_coldeltacor_oracle_matches_golden(oracle, golden, name, psc):
+    g = golden("coldeltacor_small.npz")
+    e, z, ixs = g["e"], g["z"], g["ixs"]
+    d = _d(z, name, psc)
+    tag = f"{name}_{psc:g}"
+    full = oracle.coldeltacor(e, d, None, name, psc, threads=2)
+    part = oracle.coldeltacor(e, d, ixs, name, psc, threads=2)
+    # pairs of identical columns (i == c, or the duplicated cell) have a zero-variance A: the reference
+    # returns NaN or rounding garbage there depending on the variant; callers overwrite them
+    # (analysis.py:1604-1612, 1666).  Everything else must agree to fp64 rounding.
+    ok = ~_degenerate_pairs(e)
+    for got, want in ((full, g[f"full_{tag}"]), (part, g[f"partial_{tag}"])):
+        assert not np.isnan(got[ok]).any() and not np.isnan(want[ok]).any()
+        np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=2e-12)
+    # the partial sqrt variant zeroes exact-zero differences -> NaN on identical columns in both
+    if name == "sqrt":
+        deg = ~ok
+        assert np.array_equal(np.isnan(part[deg]), np.isnan(g[f"partial_{tag}"][deg]))
+    # partial touches only the sampled entries
+    mask = np.zeros_like(part, dtype=bool)
+    mask[np.arange(ixs.shape[0])[:, None], ixs] = True
+    assert np.all(part[~mask] == 0)
+
+
+@pytest.mark.parametrize("name,psc", CASES)
+def test_coldeltacor_oracle_matches_live_reference(oracle, name, psc):
+    if oracle.load_ref_speedboosted() is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(42)
+    G, C, m = 211, 67, 19
+    e = rng.gamma(2.0, 1.0, (G, C))
+    d = _d(rng.normal(size=(G, C)), name, psc)
+    ixs = np.stack([rng.choice(C, m, replace=False) for _ in range(C)])
+    for ix in (None, ixs):
+        got = oracle.coldeltacor(e, d, ix, name, psc)
+        want = oracle.ref_coldeltacor(e, d, ix, name, psc)
+        off = ~np.eye(C, dtype=bool)      # diagonals are degenerate (NaN or rounding garbage) in both
+        if ix is not None:
+            sampled = np.zeros((C, C), dtype=bool)
+            sampled[np.arange(C)[:, None], ix] = True
+            assert np.all(got[~sampled] == 0) and np.all(want[~sampled] == 0)   # only sampled entries are touched
+            off &= sampled
+        assert not np.isnan(got[off]).any() and not np.isnan(want[off]).any()
+        np.testing.assert_allclose(got[off], want[off], rtol=0, atol=5e-13)
+
+
+def test_fit_slopes_oracle_matches_golden(oracle, golden):
+    g = golden("fit_slopes_small.npz")
+    X, Y, W = g["X"], g["Y"], g["W"]
+    eq = dict(rtol=1e-6, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(oracle.fit_slope(Y, X), g["slope"], **eq)
+    s, q = oracle.fit_slope_offset(Y, X)
+    np.testing.assert_allclose(s, g["slope_offset_g"], **eq)
+    np.testing.assert_allclose(q, g["slope_offset_q"], **eq)
+    s, q = oracle.fit_slope_offset(Y, X, fixperc_q=True)
+    np.testing.assert_allclose(s, g["slope_offset_fix_g"], **eq)
+    np.testing.assert_allclose(q, g["slope_offset_fix_q"], **eq)
+    s, r2 = oracle.fit_slope_weighted(Y, X, W, return_R2=True)
+    np.testing.assert_allclose(s, g["weighted_g"], **eq)
+    np.testing.assert_allclose(r2, g["weighted_R2"], **eq)
+    np.testing.assert_allclose(oracle.fit_slope_weighted(Y, X, W, limit_gamma=True), g["weighted_lim_g"], **eq)
+    s, q, r2 = oracle.fit_slope_weighted_offset(Y, X, W, return_R2=True)
+    np.testing.assert_allclose(s, g["weighted_offset_g"], **eq)
+    np.testing.assert_allclose(q, g["weighted_offset_q"], **eq)
+    np.testing.assert_allclose(r2, g["weighted_offset_R2"], **eq)
+    s, q = oracle.fit_slope_weighted_offset(Y, X, W, fixperc_q=True, return_R2=False)
+    np.testing.assert_allclose(s, g["weighted_offset_fix_g"], **eq)
+    np.testing.assert_allclose(q, g["weighted_offset_fix_q"], **eq)
+    # degenerate genes: x == 0 -> NaN, y == 0 -> 0 (estimation.py:176-179)
+    assert np.isnan(g["slope"][2]) and g["slope"][5] == 0
+
+
+def test_knn_smoothing_oracle_matches_golden(oracle, golden):
+    g = golden("knn_smoothing_small.npz")
+    C = g["S"].shape[1]
+    knn = sparse.csr_matrix((g["knn_data"], g["knn_indices"], g["knn_indptr"]), shape=(C, C))
+    for diag in (1, 8):
+        Sx, Ux, w = oracle.knn_imputation(g["S"], g["U"], knn, diag=diag)
+        np.testing.assert_allclose(sparse.csr_matrix(w).toarray(), g[f"w_dense_diag{diag}"], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(Sx, g[f"Sx_diag{diag}"], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(Ux, g[f"Ux_diag{diag}"], rtol=1e-13, atol=1e-13)
+
+
+def test_pipeline_oracle_matches_golden(oracle, golden):
+    g = golden("pipeline_small.npz")
+    C = g["S_sz"].shape[1]
+    knn = sparse.csr_matrix((g["knn_data"], g["knn_indices"], g["knn_indptr"]), shape=(C, C))
+    Sx, Ux, _ = oracle.knn_imputation(g["S_sz"], g["U_sz"], knn, diag=1)
+    np.testing.assert_allclose(Sx, g["Sx_sz"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(Ux, g["Ux_sz"], rtol=1e-13, atol=1e-13)
+    Sx, Ux = g["Sx_sz"], g["Ux_sz"]
+    np.testing.assert_allclose(oracle.fit_slope(Ux, Sx), g["gammas_nnls"], rtol=1e-6)
+    gam, q = oracle.fit_slope_offset(Ux, Sx)
+    np.testing.assert_allclose(gam, g["gammas_ols"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(q, g["q_ols"], rtol=1e-6, atol=1e-8)
+    W = oracle.gamma_fit_weights("maxmin_diag", Sx, Ux, Sx, Ux)
+    gd, qd, r2 = oracle.fit_slope_weighted_offset(Ux, Sx, W, return_R2=True)
+    np.testing.assert_allclose(gd, g["gammas_default"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(qd, g["q_default"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(r2, g["R2_default"], rtol=1e-5, atol=1e-7)
+    Upred = oracle.predict_U(gam.astype(np.float32), Sx, q.astype(np.float32))
+    np.testing.assert_allclose(Upred, g["Upred"], rtol=1e-12, atol=1e-12)
+    vel = oracle.calculate_velocity(Ux, Upred)
+    np.testing.assert_allclose(vel, g["velocity"], rtol=1e-12, atol=1e-12)
+    dS = oracle.calculate_shift(vel, 1.0)
+    np.testing.assert_allclose(dS, g["delta_S"], rtol=1e-12, atol=1e-12)
+    St = oracle.extrapolate_cell_at_t(Sx, dS, 1.0)
+    np.testing.assert_allclose(St, g["Sx_sz_t"], rtol=1e-12, atol=1e-12)
+    # estimate_transition_prob, knn_random mode (analysis.py:1528-1612)
+    psc = 1.0
+    neigh = g["neigh_ixs"].astype(np.int64)
+    for dkey, ckey, pkey in (("delta_S", "corrcoef", "transition_prob"),
+                             ("delta_S_rndm", "corrcoef_random", "transition_prob_random")):
+        delta = (Sx + 1.0 * g[dkey]) - Sx
+        corr = oracle.colDeltaCorSqrtpartial(Sx, oracle.velocity_transform(delta, "sqrt", psc), neigh, psc=psc)
+        oracle.patch_corrcoef(corr)
+        np.testing.assert_allclose(corr, g[ckey], rtol=0, atol=1e-12)
+        tp = oracle.transition_prob(corr, oracle.neighbors_to_csr(neigh), 0.05)
+        np.testing.assert_allclose(tp, g[pkey], rtol=1e-9, atol=1e-15)
+    de = oracle.embedding_shift(g["transition_prob"], g["embedding"], oracle.neighbors_to_csr(neigh))
+    np.testing.assert_allclose(de, g["delta_embedding"], rtol=1e-9, atol=1e-12)
+    # full mode (analysis.py:1613-1668)
+    delta = (Sx + 1.0 * g["delta_S"]) - Sx
+    corr = oracle.colDeltaCorSqrt(Sx, oracle.velocity_transform(delta, "sqrt", psc), psc=psc)
+    np.fill_diagonal(corr, 0)
+    # cells 7 and 22 converge to identical profiles after imputation: a zero-variance column, where the
+    # full sqrt variant returns rounding garbage (no zero rule, speedboosted.pyx:110-114) -- excluded.
+    ok = ~_degenerate_pairs(Sx)
+    assert (~ok).sum() == C + 2
+    np.testing.assert_allclose(corr[ok], g["full_corrcoef"][ok], rtol=0, atol=1e-12)
+    fk = g["full_knn_indices"]
+    mask = sparse.csr_matrix((np.ones(fk.size), fk.ravel(), np.arange(0, fk.size + 1, fk.shape[1])), shape=(C, C))
+    tp = oracle.transition_prob(np.where(ok | np.eye(C, dtype=bool), corr, g["full_corrcoef"]), mask, 0.05)
+    np.testing.assert_allclose(tp, g["full_transition_prob"], rtol=1e-9, atol=1e-15)
+
+
+def test_sampler_matches_golden(oracle, golden):
+    """np.random.choice stream of the neighbour sampler (analysis.py:1552-1566)."""
+    from sklearn.neighbors import NearestNeighbors
+    g = golden("pipeline_small.npz")
+    nn = NearestNeighbors(n_neighbors=31, n_jobs=1).fit(g["embedding"])
+    knn_idx = nn.kneighbors_graph(mode="connectivity").indices.reshape(-1, 31)
+    neigh, samp = oracle.sample_neighbors(knn_idx, 0.5, (0.5, 0.1), 15071990)
+    assert np.array_equal(samp, g["sampling_ixs"])
+    assert np.array_equal(neigh, g["neigh_ixs"])
