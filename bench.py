@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: cells/sec through estimate_transition_prob (colDeltaCor*partial).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the transition-probability core (per-cell velocity statistics, the
+colDeltaCorSqrtpartial correlation kernel, the softmax epilogue; plus the all-gather of the
+expression blocks when N > 1) over the whole synthetic workload of BASELINE config 4:
+100k cells x 30k genes, m = 3000 sampled neighbours per cell, transform "sqrt".  Strong scaling:
+the total problem is fixed, cells are sharded across the N ranks.
+
+One JSON line on stdout (rank 0).  ``value`` = cells / max-over-ranks device time with inputs
+resident in HBM; ``e2e`` = same metric through the host-buffer C-ABI call (H2D of e, d, ixs and
+D2H of the result inside the timed region); ``roofline`` = algorithmic bytes C*(m+2)*G*4 of the
+correlation kernel / its CUDA-event time vs the measured HBM peak; ``cpu_baseline`` = the
+reference's own compiled kernel (oracle/_ref) on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cells/sec through estimate_transition_prob (colDeltaCorSqrtpartial + transition_prob)"
+UNIT = "cells/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=100_000)
+    ap.add_argument("--genes", type=int, default=30_000)
+    ap.add_argument("--neighbors", type=int, default=3_000)
+    ap.add_argument("--psc", type=float, default=1.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of one CPU sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_sample(G, m_full, psc, seconds, steps=1, warmup=0):
+    """Time the reference's own compiled kernel (oracle/_ref) -- or the oracle port -- on the host cores.
+
+    Sample: same gene count and data distribution as the workload, fewer cells/neighbours; the rate
+    in pair*gene/s is converted to cells/s at the workload's (G, m) by exact op-count scaling."""
+    import numpy as np
+    from oracle import velo_oracle as vo
+    cores = vo.host_threads()
+    kind = "reference" if vo.load_ref_speedboosted() is not None else "port"
+    rate_guess = 0.055e9 * cores                       # pair*gene/s, SURVEY.md section 6
+    m_s = 256
+    C_s = int(max(m_s + 64, min(4096, seconds * rate_guess / (G * m_s))))
+    rng = np.random.default_rng(0)
+    e = rng.gamma(2.0, 1.0, (G, C_s))
+    e[rng.uniform(size=e.shape) < 0.3] = 0.0
+    z = rng.normal(size=(G, C_s))
+    d = np.sqrt(np.abs(z) + psc) * np.sign(z)
+    ixs = np.stack([(c + 1 + rng.choice(C_s - 1, m_s, replace=False)) % C_s for c in range(C_s)]).astype(np.int64)
+    fn = vo.ref_coldeltacor if kind == "reference" else vo.coldeltacor
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        fn(e, d, ixs, "sqrt", psc, threads=cores)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    pair_gene_per_s = G * C_s * m_s / t
+    cells_per_s = pair_gene_per_s / (G * m_full)
+    sample = (f"colDeltaCorSqrtpartial G={G} C={C_s} m={m_s} fp64, {cores} threads, {t:.2f} s/step "
+              f"({pair_gene_per_s / 1e9:.3f} G pair*gene/s); cells/s scaled by op count to m={m_full}")
+    return {"value": cells_per_s, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+            "seconds_per_step": t, "pair_gene_per_s": pair_gene_per_s}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_sample(args.genes, args.neighbors, args.psc, args.cpu_seconds, steps=args.steps,
+                              warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.cells} cells x {args.genes} genes, m={args.neighbors}, transform=sqrt "
+                               f"(BASELINE config 4); CPU arm runs a bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def synth_block(torch, dev, nc, G, m, C, c0, seed, psc):
+    """Synthetic cell block, generated on the device: e ~ Gamma(2,1) with 30% zeros, d = sign(z)sqrt(|z|+psc),
+    ixs = m uniform neighbours != self (worst case for locality: a pure HBM gather)."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    e = dev.CellMajor.empty(nc, G)
+    d = dev.CellMajor.empty(nc, G)
+    blk = 4096
+    for r0 in range(0, nc, blk):
+        n = min(blk, nc - r0)
+        u1 = torch.rand((n, G), device="cuda", generator=gen).clamp_min_(1e-7)
+        u2 = torch.rand((n, G), device="cuda", generator=gen).clamp_min_(1e-7)
+        v = -(torch.log(u1) + torch.log(u2))
+        v[torch.rand((n, G), device="cuda", generator=gen) < 0.3] = 0
+        e.t[r0:r0 + n, :G] = v
+        z = torch.randn((n, G), device="cuda", generator=gen)
+        d.t[r0:r0 + n, :G] = torch.sign(z) * torch.sqrt(z.abs() + psc)
+        del u1, u2, v, z
+    ix = ((torch.arange(c0, c0 + nc, device="cuda")[:, None] + 1 +
+           torch.randint(0, C - 1, (nc, m), device="cuda", generator=gen)) % C).to(torch.int32).contiguous()
+    return e, d, ix
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from velocyto_b200 import _cabi, device as dev
+    from velocyto_b200.sharding import CellShardedTransitionProb
+
+    C, G, m, psc, sigma = args.cells, args.genes, args.neighbors, args.psc, 0.05
+    core = CellShardedTransitionProb(G, C, "sqrt", psc, sigma)
+    e_loc, d_loc, ix_loc = synth_block(torch, dev, core.nc, G, m, C, core.c0, 1234 + rank, psc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for _ in range(args.warmup):
+        core.run(e_loc, d_loc, ix_loc)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.launch_count()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        out = core.run(e_loc, d_loc, ix_loc, kernel_events=ev[k])
+    t_stop.record()
+    barrier()
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_stop)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    tt = torch.tensor([ms_total, ms_kernel], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = float(tt[0]) / args.steps
+    ms_kernel = float(tt[1])
+    value = C / (ms_step * 1e-3)
+    checksum = float(out.sum())                         # every row sums to 1 -> equals the local cell count
+    assert abs(checksum - core.nc) < 1e-3 * max(1, core.nc), f"transition rows do not sum to 1 ({checksum} vs {core.nc})"
+
+    # ---------------- roofline of the dominant kernel (algorithmic bytes) ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = core.nc * (m + 2) * G * 4 + core.nc * m * 4          # per launch (this rank's cells)
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_coldeltacor_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_coldeltacor<SQRT,PARTIAL>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel}
+
+    # ---------------- e2e: host buffers through the C ABI (N == 1) / the sharded host API (N > 1) -------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(torch, dist, dev, _cabi, core, e_loc, d_loc, ix_loc, args, world, rank)
+        except Exception as exc:                          # e.g. not enough pinnable host memory on the box
+            e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu and world == 1:
+        del e_loc, d_loc
+        torch.cuda.empty_cache()
+        cpu = cpu_reference_sample(G, m, psc, args.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{C} cells x {G} genes, m={m} uniform-random neighbours, transform=sqrt psc={psc:g} "
+                                   f"(BASELINE config 4), cell-sharded x{world}",
+                       "l2": "inputs (12 GB expression matrix, random row gather) exceed the 126 MB L2; no flush needed",
+                       "step": "all-gather(e) [N>1] + cell_stats + k_coldeltacor + transition_prob"},
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, dist, dev, _cabi, core, e_loc, d_loc, ix_loc, args, world, rank):
+    """Same metric end to end from HOST buffers in the reference's own format: gene-major fp64 e and d,
+    int64 ixs (pinned), result read back to the host, all inside the timed region."""
+    import numpy as np
+    G, C, m = core.G, core.C, ix_loc.shape[1]
+    nc = core.nc
+    # host copies of this rank's block in the reference layout (G x nc, fp64), built from the device data
+    e_h = torch.empty((G, nc), dtype=torch.float64, pin_memory=True)
+    d_h = torch.empty((G, nc), dtype=torch.float64, pin_memory=True)
+    blk = 2048
+    for g0 in range(0, G, blk):
+        g1 = min(G, g0 + blk)
+        e_h[g0:g1].copy_(e_loc.t[:, g0:g1].t().contiguous().to(torch.float64))
+        d_h[g0:g1].copy_(d_loc.t[:, g0:g1].t().contiguous().to(torch.float64))
+    ix_h = torch.empty((nc, m), dtype=torch.int64, pin_memory=True)
+    ix_h.copy_(ix_loc)
+    out_h = torch.empty((nc, m), dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
+    h2d = e_h.numel() * 8 + d_h.numel() * 8 + ix_h.numel() * 8
+    d2h = out_h.numel() * 4
+
+    def step():
+        if world == 1:
+            # the reference-facing C-ABI call with host pointers (host tier of include/velo_b200.h)
+            _cabi.call("velo_transition_prob_partial", _cabi.SQRT, e_h.data_ptr(), d_h.data_ptr(), 8,
+                       ix_h.data_ptr(), out_h.data_ptr(), G, C, m, float(core.psc), float(core.sigma))
+        else:
+            e_dev = dev.CellMajor.from_gene_major(e_h)
+            d_dev = dev.CellMajor.from_gene_major(d_h)
+            ix_dev = ix_h.to("cuda", non_blocking=True).to(torch.int32)
+            out_h.copy_(core.run(e_dev, d_dev, ix_dev), non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step()                                               # warm-up (allocator pools, page faults)
+    barrier()
+    n = max(1, min(2, args.steps))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    barrier()
+    dt = torch.tensor([(time.perf_counter() - t0) / n], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt[0])
+    return {"value": C / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": sec * 1e3, "steps": n,
+            "api": "velo_transition_prob_partial (C ABI, host fp64 gene-major)" if world == 1
+                   else "CellMajor.from_gene_major + CellShardedTransitionProb.run (host fp64 blocks)"}
+
+
+if __name__ == "__main__":
+    main()

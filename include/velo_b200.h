@@ -1,0 +1,153 @@
+/*
+ * velo_b200.h -- C ABI of libvelo_b200.so, the B200-native (sm_100a) numerical
+ * core behind VelocytoLoom.{knn_imputation, fit_gammas, predict_U,
+ * estimate_transition_prob} of velocyto.py 0.17.16.
+ *
+ * Two tiers of entry points:
+ *
+ *  (1) HOST drop-ins  (velo_colDeltaCor*): same argument lists as the reference's
+ *      native functions `x_colDeltaCor*` (velocyto/speedboosted.pyx:13-538, reached
+ *      through the Python-callable `_colDeltaCor*` at speedboosted.pyx:542-610) --
+ *      host pointers, gene-major (rows = genes) row-major fp64 matrices, output
+ *      ACCUMULATED into the caller-zeroed dense cells x cells fp64 `rm`.  Sizes are
+ *      64-bit (the reference's C `int` overflows at genes*cells >= 2^31).
+ *      `num_threads` is accepted and ignored.  These are what a maintainer binds in
+ *      place of `velocyto.speedboosted`.
+ *
+ *  (2) DEVICE tier (velo_dev_*): device pointers + a CUDA stream; matrices are
+ *      CELL-MAJOR fp32 (`x[cell * ld + gene]`, ld % 4 == 0, pad columns zero), the
+ *      layout the kernels are designed around (a cell's expression profile is one
+ *      contiguous, 16-byte aligned row).  Outputs are compact (cells x m) instead of
+ *      dense cells x cells.  The Python host layer (velocyto.py_b200) keeps data
+ *      resident in HBM between the four methods through this tier.
+ *
+ * Every function returns 0 on success, or a negative VELO_E_* code; the message of
+ * the last failure on the calling thread is available from velo_last_error().
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef VELO_B200_H
+#define VELO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VELO_ABI_VERSION 1
+
+/* status codes */
+#define VELO_OK            0
+#define VELO_E_INVALID    -1   /* bad argument (shape, alignment, enum) */
+#define VELO_E_CUDA       -2   /* CUDA runtime error (see velo_last_error) */
+#define VELO_E_NODEVICE   -3   /* no sm_100-class device visible */
+#define VELO_E_NOMEM      -4   /* device allocation failed */
+
+/* transform applied to the expression difference (the three reference families) */
+#define VELO_LINEAR 0          /* colDeltaCor       / colDeltaCorpartial        */
+#define VELO_SQRT   1          /* colDeltaCorSqrt   / colDeltaCorSqrtpartial    */
+#define VELO_LOG10  2          /* colDeltaCorLog10  / colDeltaCorLog10partial   */
+
+/* zero rule: the reference's full and partial loops treat t == 0 differently
+ * (speedboosted.pyx:110-114,195-199 vs :372-378,470-473); see DESIGN.md. */
+#define VELO_RULE_FULL    0
+#define VELO_RULE_PARTIAL 1
+
+typedef void *velo_stream_t;   /* a cudaStream_t; NULL = legacy default stream */
+
+/* ---------------------------------------------------------------- library --- */
+int         velo_abi_version(void);
+const char *velo_last_error(void);
+/* sm count, opt-in shared memory per block, total HBM bytes of the current device */
+int         velo_device_info(int *sm_count, int *smem_optin_bytes, size_t *hbm_bytes,
+                             int *cc_major, int *cc_minor);
+/* number of kernel launches issued by this library in this process (bench evidence) */
+uint64_t    velo_launch_count(void);
+
+/* ------------------------------------------------- (1) host drop-in tier --- */
+/* replaces x_colDeltaCor            speedboosted.pyx:13-87   (_colDeltaCor :542-550) */
+int velo_colDeltaCor(const double *e, const double *d, double *rm,
+                     int64_t rows, int64_t cols, int num_threads);
+/* replaces x_colDeltaCorSqrt        speedboosted.pyx:93-172  (_colDeltaCorSqrt :552-561) */
+int velo_colDeltaCorSqrt(const double *e, const double *d, double *rm,
+                         int64_t rows, int64_t cols, int num_threads, double psc);
+/* replaces x_colDeltaCorLog10       speedboosted.pyx:178-257 (_colDeltaCorLog10 :563-572) */
+int velo_colDeltaCorLog10(const double *e, const double *d, double *rm,
+                          int64_t rows, int64_t cols, int num_threads, double psc);
+/* replaces x_colDeltaCorpartial     speedboosted.pyx:263-346 (_colDeltaCorpartial :574-584) */
+int velo_colDeltaCorpartial(const double *e, const double *d, double *rm, const int64_t *ixs,
+                            int64_t rows, int64_t cols, int64_t nrndm, int num_threads);
+/* replaces x_colDeltaCorSqrtpartial speedboosted.pyx:352-443 (_colDeltaCorSqrtpartial :586-597) */
+int velo_colDeltaCorSqrtpartial(const double *e, const double *d, double *rm, const int64_t *ixs,
+                                int64_t rows, int64_t cols, int64_t nrndm, int num_threads,
+                                double psc);
+/* replaces x_colDeltaCorLog10partial speedboosted.pyx:449-538 (_colDeltaCorLog10partial :599-610) */
+int velo_colDeltaCorLog10partial(const double *e, const double *d, double *rm, const int64_t *ixs,
+                                 int64_t rows, int64_t cols, int64_t nrndm, int num_threads,
+                                 double psc);
+
+/* Same computation as the partial drop-ins, compact output: out[c*nrndm + n] =
+ * corr(cell c, its n-th sampled neighbour), fp32, NaN where the reference gives NaN.
+ * The dense cells x cells result of the reference does not exist at 100k cells (80 GB).
+ * e, d: host, gene-major rows x cols, fp64 (elem_bytes = 8) or fp32 (elem_bytes = 4). */
+int velo_colDeltaCorpartial_compact(int transform, const void *e, const void *d, int elem_bytes,
+                                    const int64_t *ixs, float *out,
+                                    int64_t rows, int64_t cols, int64_t nrndm, double psc);
+/* The whole estimate_transition_prob numeric core in one host call: the compact correlations
+ * above followed by the transition-probability epilogue (analysis.py:1604-1612, 1697-1698):
+ * out[c*nrndm + n] = P(c -> ixs[c, n]).  sigma = sigma_corr of calculate_embedding_shift. */
+int velo_transition_prob_partial(int transform, const void *e, const void *d, int elem_bytes,
+                                 const int64_t *ixs, float *out,
+                                 int64_t rows, int64_t cols, int64_t nrndm, double psc, double sigma);
+
+/* ---------------------------------------------------- (2) device tier ------ */
+/* gene-major (G x C, row-major, host layout of the reference) -> cell-major fp32
+ * dst[c * ld + g], c in [0,C), g in [g_off, g_off+G); pad columns are NOT touched.
+ * src is a DEVICE pointer; elem_bytes 8 (fp64) or 4 (fp32). */
+int velo_dev_pack_cellmajor(const void *src_gc, int elem_bytes, int64_t G, int64_t C,
+                            float *dst_cg, int64_t ld, int64_t g_off, velo_stream_t stream);
+/* cell-major fp32 -> gene-major fp64/fp32 (inverse of the above, for results that
+ * go back to the reference's attribute layout) */
+int velo_dev_unpack_genemajor(const float *src_cg, int64_t ld, int64_t G, int64_t C,
+                              void *dst_gc, int elem_bytes, velo_stream_t stream);
+int velo_dev_i64_to_i32(const int64_t *src, int32_t *dst, int64_t n, velo_stream_t stream);
+
+/* per-cell mean and centred sum of squares of the velocity rows:
+ * stats[2*r] = mean_g d[r, g], stats[2*r+1] = sum_g (d[r, g] - mean)^2
+ * (speedboosted.pyx:46-55, 67-72).  d_cm: nc x ld. */
+int velo_dev_cell_stats(const float *d_cm, int64_t ld, int64_t G, int64_t nc,
+                        float *stats, velo_stream_t stream);
+
+/* The correlation kernel (K1).  For local cells r in [0, nc) (global id c0 + r):
+ *   out[r * out_ld + n] = pearson_g( f(e[i, g] - e[c0 + r, g]), d[r, g] ),
+ *   i = ixs[r * ixs_ld + n]   (ixs != NULL, n < m)      -- "partial"
+ *   i = n                      (ixs == NULL, m == C)     -- "full"
+ * e_cm : C x ld cell-major fp32 (ALL cells: neighbours may be any cell)
+ * d_cm : nc x ld (rows of the local cells only), stats from velo_dev_cell_stats
+ * rule : VELO_RULE_PARTIAL or VELO_RULE_FULL (zero rule of the variant)
+ * Workspace-free.  One launch. */
+int velo_dev_coldeltacor(int transform, int rule,
+                         const float *e_cm, const float *d_cm, int64_t ld,
+                         const float *stats, const int32_t *ixs, int64_t ixs_ld,
+                         float *out, int64_t out_ld,
+                         int64_t G, int64_t C, int64_t c0, int64_t nc, int64_t m,
+                         double psc, velo_stream_t stream);
+
+/* rm[(c0 + r) * C + i] += out[r, n]  (dense adapter for small C; fp64 atomics so that
+ * duplicated indices accumulate as in the reference, speedboosted.pyx:336) */
+int velo_dev_scatter_dense(const float *out, int64_t out_ld, const int32_t *ixs, int64_t ixs_ld,
+                           double *rm, int64_t C, int64_t c0, int64_t nc, int64_t m,
+                           velo_stream_t stream);
+
+/* transition probabilities, compact form of analysis.py:1604-1612 + 1697-1698:
+ * corr patched (self -> 0, NaN -> 1), p[r, n] = exp(corr/sigma) / sum_n exp(corr/sigma).
+ * ixs == NULL means neighbour n is cell n (full mode). In place allowed (p == corr). */
+int velo_dev_transition_prob(const float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld,
+                             float *p, int64_t p_ld, int64_t c0, int64_t nc, int64_t m,
+                             double sigma, velo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELO_B200_H */

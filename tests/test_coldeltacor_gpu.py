@@ -1,0 +1,243 @@
+"""GPU parity of the colDeltaCor kernels against the oracle and the reference golden vectors.
+
+Everything goes through the C ABI (host tier via ``velocyto_b200.estimation``, device tier via
+``velocyto_b200.device``).  Tolerances: the north-star bar is 1e-5 relative on transition
+probabilities; ``p ~ exp(corr / 0.05)`` amplifies an absolute correlation error 20x, so the
+correlations themselves are held to 5e-7 absolute (2e-6 on the tiny golden case with 37 genes,
+where single fp32 roundings are not averaged out).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("sqrt", 1e-10), ("sqrt", 1.0), ("log10", 1.0), ("log10", 0.5), ("linear", 0.0)]
+
+
+def _d(z, name, psc):
+    if name == "sqrt":
+        return np.sqrt(np.abs(z) + psc) * np.sign(z)
+    if name == "log10":
+        return np.log10(np.abs(z) + psc) * np.sign(z)
+    return z
+
+
+def _api(name, partial):
+    import velocyto_b200.estimation as est
+    return {("linear", False): est.colDeltaCor, ("linear", True): est.colDeltaCorpartial,
+            ("sqrt", False): est.colDeltaCorSqrt, ("sqrt", True): est.colDeltaCorSqrtpartial,
+            ("log10", False): est.colDeltaCorLog10, ("log10", True): est.colDeltaCorLog10partial}[(name, partial)]
+
+
+def _call(name, partial, e, d, ixs, psc, **kw):
+    fn = _api(name, partial)
+    args = (e, d, ixs) if partial else (e, d)
+    if name != "linear":
+        kw["psc"] = psc
+    return fn(*args, **kw)
+
+
+def _degenerate_pairs(e):
+    C = e.shape[1]
+    return np.array([[np.array_equal(e[:, i], e[:, c]) for i in range(C)] for c in range(C)])
+
+
+def synth(G, C, seed, name="sqrt", psc=1e-10):
+    rng = np.random.default_rng(seed)
+    e = rng.gamma(2.0, 1.0, (G, C))
+    e[rng.uniform(size=(G, C)) < 0.3] = 0.0          # realistic sparsity -> exact zero differences
+    d = _d(rng.normal(size=(G, C)), name, psc)
+    return e, d
+
+
+def rand_ixs(C, m, seed):
+    """m distinct neighbours per cell, never the cell itself (a self pair is a zero-variance column:
+    NaN or rounding garbage in the reference depending on the variant)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((C, m), dtype=np.int64)
+    for c in range(C):
+        pick = rng.choice(C - 1, m, replace=False)
+        out[c] = pick + (pick >= c)
+    return out
+
+
+@pytest.mark.parametrize("name,psc", CASES)
+def test_golden_small_all_variants(golden, name, psc):
+    g = golden("coldeltacor_small.npz")
+    e, z, ixs = g["e"], g["z"], g["ixs"]
+    d = _d(z, name, psc)
+    tag = f"{name}_{psc:g}"
+    ok = ~_degenerate_pairs(e)
+    full = _call(name, False, e, d, None, psc)
+    part = _call(name, True, e, d, ixs, psc)
+    assert full.shape == part.shape == (e.shape[1],) * 2 and full.dtype == np.float64
+    for got, want in ((full, g[f"full_{tag}"]), (part, g[f"partial_{tag}"])):
+        assert not np.isnan(got[ok]).any()
+        np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=2e-6)
+    sampled = np.zeros_like(ok)
+    sampled[np.arange(ixs.shape[0])[:, None], ixs] = True
+    assert np.all(part[~sampled] == 0)                # only sampled entries are touched
+    if name == "sqrt":                                # zero rule -> NaN on identical columns, as the reference
+        deg = ~ok & sampled
+        assert np.array_equal(np.isnan(part[deg]), np.isnan(g[f"partial_{tag}"][deg]))
+
+
+@pytest.mark.parametrize("name,psc", CASES)
+def test_partial_matches_oracle_medium(oracle, name, psc):
+    G, C, m = 2000, 600, 96
+    e, d = synth(G, C, 1, name, psc)
+    ixs = rand_ixs(C, m, 2)
+    want = oracle.coldeltacor(e, d, ixs, name, psc)
+    got = _call(name, True, e, d, ixs, psc)
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-7)
+    comp = _call(name, True, e, d, ixs, psc, compact=True)
+    assert comp.shape == (C, m) and comp.dtype == np.float32
+    np.testing.assert_allclose(comp, want[np.arange(C)[:, None], ixs], rtol=0, atol=5e-7)
+
+
+@pytest.mark.parametrize("name,psc", CASES)
+def test_full_matches_oracle_medium(oracle, name, psc):
+    G, C = 1500, 257
+    e, d = synth(G, C, 3, name, psc)
+    want = oracle.coldeltacor(e, d, None, name, psc)
+    got = _call(name, False, e, d, None, psc)
+    off = ~np.eye(C, dtype=bool)                      # the diagonal is degenerate in every full variant
+    np.testing.assert_allclose(got[off], want[off], rtol=0, atol=5e-7)
+
+
+@pytest.mark.parametrize("G", [30001, 61003, 129, 3])
+def test_ragged_and_multislab_gene_axis(oracle, G):
+    """G not a multiple of 4/128, and G large enough for 2 and 3 shared-memory slabs."""
+    C, m = 24, 7
+    e, d = synth(G, C, 4, "sqrt", 1.0)
+    ixs = rand_ixs(C, m, 5)
+    want = oracle.coldeltacor(e, d, ixs, "sqrt", 1.0)
+    got = _call("sqrt", True, e, d, ixs, 1.0)
+    np.testing.assert_allclose(got, want, rtol=0, atol=(5e-7 if G > 100 else 5e-6))
+
+
+def test_more_neighbours_than_one_chunk(oracle):
+    """m > 4096 exercises the neighbour-chunk loop of the kernel."""
+    G, C, m = 48, 4300, 4200
+    e, d = synth(G, C, 6, "linear", 0.0)
+    rng = np.random.default_rng(7)
+    ixs = np.stack([rng.permutation(C)[:m] for _ in range(C)])
+    want = oracle.coldeltacor(e, d, ixs, "linear", 0.0)
+    got = _call("linear", True, e, d, ixs, 0.0, compact=True)
+    ref = want[np.arange(C)[:, None], ixs]
+    ok = ixs != np.arange(C)[:, None]
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=0, atol=5e-6)
+
+
+def test_duplicate_indices_accumulate(oracle):
+    """`rm[c, i] +=` per sampled slot: a repeated index counts twice (speedboosted.pyx:336)."""
+    G, C, m = 300, 40, 6
+    e, d = synth(G, C, 8, "sqrt", 1.0)
+    ixs = rand_ixs(C, m, 9)
+    ixs[:, 1] = ixs[:, 0]
+    want = oracle.coldeltacor(e, d, ixs, "sqrt", 1.0)
+    got = _call("sqrt", True, e, d, ixs, 1.0)
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want), rtol=0, atol=1e-6)
+
+
+def test_reference_argument_contract():
+    """dmat must already be C-contiguous float64; emat / ixs are coerced (estimation.py:59-60)."""
+    import velocyto_b200.estimation as est
+    G, C, m = 64, 16, 4
+    e, d = synth(G, C, 10)
+    ixs = rand_ixs(C, m, 0)
+    with pytest.raises(ValueError):
+        est.colDeltaCorSqrtpartial(e, np.asfortranarray(d), ixs, psc=1.0)
+    with pytest.raises(ValueError):
+        est.colDeltaCorSqrtpartial(e, d.astype(np.float32), ixs, psc=1.0)
+    a = est.colDeltaCorSqrtpartial(np.asfortranarray(e), d, ixs.astype(np.int32), psc=1.0)
+    b = est.colDeltaCorSqrtpartial(e, d, ixs, threads=3, psc=1.0)
+    assert np.array_equal(a, b)
+    from velocyto_b200 import VeloError
+    bad = ixs.copy()
+    bad[0, 0] = C
+    with pytest.raises(VeloError):
+        est.colDeltaCorSqrtpartial(e, d, bad, psc=1.0)
+
+
+def test_device_tier_sharded_rows_match_whole(oracle):
+    """Cell-sharded call (c0, nc) == the same rows of the whole-problem call: the multi-GPU contract."""
+    import torch
+    from velocyto_b200 import device as dev
+    G, C, m = 700, 300, 33
+    e, d = synth(G, C, 11, "sqrt", 1e-10)
+    ixs = rand_ixs(C, m, 12)
+    e_cm, d_cm = dev.CellMajor.from_gene_major(e), dev.CellMajor.from_gene_major(d)
+    ix = dev.indices_to_device(ixs, C)
+    whole = dev.coldeltacor(e_cm, d_cm, ix, "sqrt", 1e-10)
+    c0, nc = 117, 90
+    part = dev.coldeltacor(e_cm, d_cm.rows(c0, nc), ix[c0:c0 + nc].contiguous(), "sqrt", 1e-10, c0=c0)
+    assert torch.equal(whole[c0:c0 + nc], part)       # bit-identical: same kernel, same order
+    want = oracle.coldeltacor(e, d, ixs, "sqrt", 1e-10)[np.arange(C)[:, None], ixs]
+    np.testing.assert_allclose(whole.cpu().numpy(), want, rtol=0, atol=5e-7)
+    # round trip of the layout converters
+    np.testing.assert_allclose(e_cm.to_gene_major(), e.astype(np.float32).astype(np.float64), rtol=0, atol=0)
+
+
+def test_transition_prob_matches_reference_golden(golden):
+    """corrcoef -> transition_prob within 1e-5 relative of the reference (analysis.py:1604-1612,1697-1698)."""
+    import torch
+    from velocyto_b200 import device as dev
+    g = golden("pipeline_small.npz")
+    Sx = g["Sx_sz"]
+    C = Sx.shape[1]
+    neigh = g["neigh_ixs"].astype(np.int64)
+    psc = 1.0
+    e_cm = dev.CellMajor.from_gene_major(Sx)
+    ix = dev.indices_to_device(neigh, C)
+    for dkey, pkey in (("delta_S", "transition_prob"), ("delta_S_rndm", "transition_prob_random")):
+        delta = (Sx + 1.0 * g[dkey]) - Sx
+        dmat = np.sqrt(np.abs(delta) + psc) * np.sign(delta)
+        corr = dev.coldeltacor(e_cm, dev.CellMajor.from_gene_major(dmat), ix, "sqrt", psc)
+        tp = dev.transition_prob(corr, ix, 0.05).cpu().numpy().astype(np.float64)
+        want = g[pkey][np.arange(C)[:, None], neigh]
+        np.testing.assert_allclose(tp, want, rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(tp.sum(1), 1.0, rtol=1e-6)
+
+
+def test_full_size_properties_and_spot_check(oracle):
+    """BASELINE config-4 shape (100k cells x 30k genes) at reduced m: size-independent properties
+    (|corr| <= 1, sign flip under d -> -d, invariance under d -> 3d, determinism) plus an oracle
+    spot check of a few cells on the gathered sub-problem."""
+    import torch
+    from velocyto_b200 import device as dev
+    free, _ = torch.cuda.mem_get_info()
+    C, G, m = (100_000, 30_000, 24) if free > 60e9 else (20_000, 8_000, 24)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    e_cm = dev.CellMajor.empty(C, G)
+    d_cm = dev.CellMajor.empty(C, G)
+    blk = 10_000
+    for c0 in range(0, C, blk):
+        u = torch.rand((min(blk, C - c0), G), device="cuda", generator=gen)
+        v = -torch.log(torch.rand_like(u).clamp_min(1e-7)) - torch.log(u.clamp_min(1e-7))   # Gamma(2,1)
+        v[torch.rand_like(u) < 0.3] = 0
+        e_cm.t[c0:c0 + v.shape[0], :G] = v
+        z = torch.randn((v.shape[0], G), device="cuda", generator=gen)
+        d_cm.t[c0:c0 + v.shape[0], :G] = torch.sign(z) * torch.sqrt(z.abs() + 1.0)
+    # m neighbours per cell, never the cell itself (a self pair is degenerate: NaN, as in the reference)
+    ix = ((torch.arange(C, device="cuda")[:, None] + 1 +
+           torch.randint(0, C - 1, (C, m), device="cuda", generator=gen)) % C).to(torch.int32).contiguous()
+    out = dev.coldeltacor(e_cm, d_cm, ix, "sqrt", 1.0)
+    assert torch.isfinite(out).all() and float(out.abs().max()) <= 1.0 + 1e-6
+    assert torch.equal(out, dev.coldeltacor(e_cm, d_cm, ix, "sqrt", 1.0))                   # deterministic
+    d_cm.t.mul_(-3.0)
+    flipped = dev.coldeltacor(e_cm, d_cm, ix, "sqrt", 1.0)
+    assert float((flipped + out).abs().max()) < 2e-6
+    d_cm.t.div_(-3.0)
+    # spot check: cells and their neighbours gathered into a small dense problem for the oracle
+    for c in (0, C // 3, C - 1):
+        nb = ix[c].cpu().numpy().astype(np.int64)
+        cols = np.concatenate([[c], nb])
+        e_sub = e_cm.t[torch.from_numpy(cols).cuda(), :G].cpu().numpy().astype(np.float64).T
+        d_sub = np.zeros_like(e_sub)
+        d_sub[:, 0] = d_cm.t[c, :G].cpu().numpy()
+        sub_ix = np.zeros((cols.size, m), dtype=np.int64)
+        sub_ix[0] = np.arange(1, m + 1)
+        d_sub[:, 1:] = 1.0 + np.arange(G)[:, None]     # any non-degenerate filler
+        want = oracle.coldeltacor(e_sub, d_sub, sub_ix, "sqrt", 1.0)[0, 1:]
+        np.testing.assert_allclose(out[c].cpu().numpy(), want, rtol=0, atol=5e-7)

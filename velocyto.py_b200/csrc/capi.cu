@@ -1,0 +1,249 @@
+// Library plumbing + the HOST drop-in tier of the C ABI (include/velo_b200.h).
+//
+// The host entry points take exactly what the reference's native functions take
+// (x_colDeltaCor*, velocyto/speedboosted.pyx:13-538): host pointers to gene-major fp64
+// matrices, an index matrix, and a dense cells x cells fp64 output that is accumulated into.
+// They stage the inputs to HBM in gene-row chunks, convert them on the device to the
+// cell-major fp32 layout of the kernels, run the same device tier the Python layer uses,
+// and bring the result back.  No host arithmetic on the data path.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "velo_common.cuh"
+
+namespace velo {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+int get_device_props(DeviceProps *out)
+{
+    static std::mutex mu;
+    static DeviceProps cache[64];
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device visible: libvelo_b200 has no CPU fallback");
+        return VELO_E_NODEVICE;
+    }
+    int dev = 0;
+    VELO_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 64 && cache[dev].device == dev) {
+        *out = cache[dev];
+        return VELO_OK;
+    }
+    cudaDeviceProp prop;
+    VELO_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    DeviceProps dp;
+    dp.device = dev;
+    dp.sm_count = prop.multiProcessorCount;
+    dp.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    dp.cc_major = prop.major;
+    dp.cc_minor = prop.minor;
+    dp.hbm_bytes = prop.totalGlobalMem;
+    if (dp.cc_major != 10) {
+        set_error("device %d is sm_%d%d; libvelo_b200 is built for sm_100a only", dev, prop.major, prop.minor);
+        return VELO_E_NODEVICE;
+    }
+    if (dev < 64) cache[dev] = dp;
+    *out = dp;
+    return VELO_OK;
+}
+
+// RAII for stream-ordered device allocations inside the host tier
+struct DevBuf {
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    int alloc(size_t bytes, cudaStream_t s)
+    {
+        st = s;
+        VELO_CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, s));
+        return VELO_OK;
+    }
+    template <typename T>
+    T *as() const
+    {
+        return static_cast<T *>(p);
+    }
+};
+
+// upload a host gene-major matrix into a cell-major fp32 device matrix, gene-row chunk by chunk
+static int upload_cellmajor(const void *host_gc, int elem_bytes, int64_t G, int64_t C, float *dst_cg, int64_t ld,
+                            cudaStream_t st)
+{
+    const int64_t row_bytes = C * elem_bytes;
+    int64_t chunk_rows = (256LL << 20) / (row_bytes > 0 ? row_bytes : 1);
+    if (chunk_rows < 32) chunk_rows = 32;
+    if (chunk_rows > G) chunk_rows = G;
+    DevBuf stage;
+    int rc = stage.alloc(static_cast<size_t>(chunk_rows * row_bytes), st);
+    if (rc) return rc;
+    for (int64_t g0 = 0; g0 < G; g0 += chunk_rows) {
+        const int64_t rows = (G - g0 < chunk_rows) ? G - g0 : chunk_rows;
+        VELO_CUDA_TRY(cudaMemcpyAsync(stage.p, static_cast<const char *>(host_gc) + g0 * row_bytes,
+                                      static_cast<size_t>(rows * row_bytes), cudaMemcpyHostToDevice, st));
+        rc = velo_dev_pack_cellmajor(stage.p, elem_bytes, rows, C, dst_cg, ld, g0, st);
+        if (rc) return rc;
+    }
+    return VELO_OK;
+}
+
+// Shared body of the host tier.  Exactly one of (rm, out_compact) is non-null.
+static int host_coldeltacor(int transform, int rule, const void *e, const void *d, int elem_bytes,
+                            const int64_t *ixs, int64_t rows, int64_t cols, int64_t nrndm, double psc, double *rm,
+                            float *out_compact, double sigma = 0.0)
+{
+    VELO_REQUIRE(e && d && (rm || out_compact), "colDeltaCor: null pointer");
+    VELO_REQUIRE(rows > 0 && cols > 0, "colDeltaCor: empty matrix (%lld x %lld)", static_cast<long long>(rows),
+                 static_cast<long long>(cols));
+    VELO_REQUIRE(ixs == nullptr || nrndm >= 0, "colDeltaCor: negative neighbour count");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const int64_t G = rows, C = cols;
+    const int64_t m = ixs ? nrndm : C;
+    if (m == 0) return VELO_OK;
+    const int64_t ld = round_up(G, 32);
+
+    cudaStream_t st;
+    VELO_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard {
+        cudaStream_t s;
+        ~StreamGuard() { cudaStreamDestroy(s); }
+    } guard{st};
+
+    DevBuf e_cm, d_cm, stats, out, ix32, ix64, rm_dev, flag;
+    if ((rc = e_cm.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
+    if ((rc = d_cm.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
+    if ((rc = stats.alloc(static_cast<size_t>(C) * 2 * 4, st))) return rc;
+    if ((rc = out.alloc(static_cast<size_t>(C * m) * 4, st))) return rc;
+    if (ld != G) {   // pad columns: defined values (never enter the sums)
+        VELO_CUDA_TRY(cudaMemsetAsync(e_cm.p, 0, static_cast<size_t>(C * ld) * 4, st));
+        VELO_CUDA_TRY(cudaMemsetAsync(d_cm.p, 0, static_cast<size_t>(C * ld) * 4, st));
+    }
+    if ((rc = upload_cellmajor(e, elem_bytes, G, C, e_cm.as<float>(), ld, st))) return rc;
+    if ((rc = upload_cellmajor(d, elem_bytes, G, C, d_cm.as<float>(), ld, st))) return rc;
+    if (ixs) {
+        if ((rc = ix64.alloc(static_cast<size_t>(C * m) * 8, st))) return rc;
+        if ((rc = ix32.alloc(static_cast<size_t>(C * m) * 4, st))) return rc;
+        if ((rc = flag.alloc(sizeof(int), st))) return rc;
+        VELO_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        VELO_CUDA_TRY(cudaMemcpyAsync(ix64.p, ixs, static_cast<size_t>(C * m) * 8, cudaMemcpyHostToDevice, st));
+        if ((rc = i64_to_i32_checked(ix64.as<int64_t>(), ix32.as<int32_t>(), C * m, C, flag.as<int>(), st))) return rc;
+        int bad = 0;   // the kernel must not gather through an out-of-range index: check before launching it
+        VELO_CUDA_TRY(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VELO_CUDA_TRY(cudaStreamSynchronize(st));
+        VELO_REQUIRE(bad == 0, "colDeltaCor: ixs holds an index outside [0, %lld)", static_cast<long long>(C));
+    }
+    if ((rc = velo_dev_cell_stats(d_cm.as<float>(), ld, G, C, stats.as<float>(), st))) return rc;
+    if ((rc = velo_dev_coldeltacor(transform, rule, e_cm.as<float>(), d_cm.as<float>(), ld, stats.as<float>(),
+                                   ixs ? ix32.as<int32_t>() : nullptr, m, out.as<float>(), m, G, C, 0, C, m, psc, st)))
+        return rc;
+    if (out_compact) {
+        if (sigma > 0.0 &&
+            (rc = velo_dev_transition_prob(out.as<float>(), m, ixs ? ix32.as<int32_t>() : nullptr, m, out.as<float>(),
+                                           m, 0, C, m, sigma, st)))
+            return rc;
+        VELO_CUDA_TRY(cudaMemcpyAsync(out_compact, out.p, static_cast<size_t>(C * m) * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+        // dense adapter: accumulate into the caller's rm (+= semantics, speedboosted.pyx:78,336)
+        if ((rc = rm_dev.alloc(static_cast<size_t>(C * C) * 8, st))) return rc;
+        VELO_CUDA_TRY(cudaMemcpyAsync(rm_dev.p, rm, static_cast<size_t>(C * C) * 8, cudaMemcpyHostToDevice, st));
+        if ((rc = velo_dev_scatter_dense(out.as<float>(), m, ixs ? ix32.as<int32_t>() : nullptr, m,
+                                         rm_dev.as<double>(), C, 0, C, m, st)))
+            return rc;
+        VELO_CUDA_TRY(cudaMemcpyAsync(rm, rm_dev.p, static_cast<size_t>(C * C) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    VELO_CUDA_TRY(cudaStreamSynchronize(st));
+    return VELO_OK;
+}
+
+}  // namespace velo
+
+using namespace velo;
+
+extern "C" int velo_abi_version(void) { return VELO_ABI_VERSION; }
+extern "C" const char *velo_last_error(void) { return t_error.c_str(); }
+extern "C" uint64_t velo_launch_count(void) { return g_launches.load(); }
+
+extern "C" int velo_device_info(int *sm_count, int *smem_optin_bytes, size_t *hbm_bytes, int *cc_major, int *cc_minor)
+{
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    if (sm_count) *sm_count = dp.sm_count;
+    if (smem_optin_bytes) *smem_optin_bytes = dp.smem_optin;
+    if (hbm_bytes) *hbm_bytes = dp.hbm_bytes;
+    if (cc_major) *cc_major = dp.cc_major;
+    if (cc_minor) *cc_minor = dp.cc_minor;
+    return VELO_OK;
+}
+
+extern "C" int velo_colDeltaCor(const double *e, const double *d, double *rm, int64_t rows, int64_t cols, int)
+{
+    return host_coldeltacor(VELO_LINEAR, VELO_RULE_FULL, e, d, 8, nullptr, rows, cols, 0, 0.0, rm, nullptr);
+}
+extern "C" int velo_colDeltaCorSqrt(const double *e, const double *d, double *rm, int64_t rows, int64_t cols, int,
+                                    double psc)
+{
+    return host_coldeltacor(VELO_SQRT, VELO_RULE_FULL, e, d, 8, nullptr, rows, cols, 0, psc, rm, nullptr);
+}
+extern "C" int velo_colDeltaCorLog10(const double *e, const double *d, double *rm, int64_t rows, int64_t cols, int,
+                                     double psc)
+{
+    return host_coldeltacor(VELO_LOG10, VELO_RULE_FULL, e, d, 8, nullptr, rows, cols, 0, psc, rm, nullptr);
+}
+extern "C" int velo_colDeltaCorpartial(const double *e, const double *d, double *rm, const int64_t *ixs, int64_t rows,
+                                       int64_t cols, int64_t nrndm, int)
+{
+    VELO_REQUIRE(ixs, "colDeltaCorpartial: ixs is NULL");
+    return host_coldeltacor(VELO_LINEAR, VELO_RULE_PARTIAL, e, d, 8, ixs, rows, cols, nrndm, 0.0, rm, nullptr);
+}
+extern "C" int velo_colDeltaCorSqrtpartial(const double *e, const double *d, double *rm, const int64_t *ixs,
+                                           int64_t rows, int64_t cols, int64_t nrndm, int, double psc)
+{
+    VELO_REQUIRE(ixs, "colDeltaCorSqrtpartial: ixs is NULL");
+    return host_coldeltacor(VELO_SQRT, VELO_RULE_PARTIAL, e, d, 8, ixs, rows, cols, nrndm, psc, rm, nullptr);
+}
+extern "C" int velo_colDeltaCorLog10partial(const double *e, const double *d, double *rm, const int64_t *ixs,
+                                            int64_t rows, int64_t cols, int64_t nrndm, int, double psc)
+{
+    VELO_REQUIRE(ixs, "colDeltaCorLog10partial: ixs is NULL");
+    return host_coldeltacor(VELO_LOG10, VELO_RULE_PARTIAL, e, d, 8, ixs, rows, cols, nrndm, psc, rm, nullptr);
+}
+extern "C" int velo_colDeltaCorpartial_compact(int transform, const void *e, const void *d, int elem_bytes,
+                                               const int64_t *ixs, float *out, int64_t rows, int64_t cols,
+                                               int64_t nrndm, double psc)
+{
+    VELO_REQUIRE(ixs && out, "colDeltaCorpartial_compact: null pointer");
+    VELO_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "colDeltaCorpartial_compact: elem_bytes must be 4 or 8");
+    VELO_REQUIRE(transform >= VELO_LINEAR && transform <= VELO_LOG10, "colDeltaCorpartial_compact: unknown transform");
+    return host_coldeltacor(transform, VELO_RULE_PARTIAL, e, d, elem_bytes, ixs, rows, cols, nrndm, psc, nullptr, out);
+}
+extern "C" int velo_transition_prob_partial(int transform, const void *e, const void *d, int elem_bytes,
+                                            const int64_t *ixs, float *out, int64_t rows, int64_t cols,
+                                            int64_t nrndm, double psc, double sigma)
+{
+    VELO_REQUIRE(ixs && out, "transition_prob_partial: null pointer");
+    VELO_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "transition_prob_partial: elem_bytes must be 4 or 8");
+    VELO_REQUIRE(transform >= VELO_LINEAR && transform <= VELO_LOG10, "transition_prob_partial: unknown transform");
+    VELO_REQUIRE(sigma > 0.0, "transition_prob_partial: sigma must be positive");
+    return host_coldeltacor(transform, VELO_RULE_PARTIAL, e, d, elem_bytes, ixs, rows, cols, nrndm, psc, nullptr, out,
+                            sigma);
+}

@@ -1,0 +1,376 @@
+// K1/K2 -- the colDeltaCor correlation kernel (all six reference variants).
+//
+// Replaces x_colDeltaCor{,Sqrt,Log10}{,partial} (velocyto/speedboosted.pyx:13-538).
+//
+// Work decomposition (one persistent CTA per SM, static striding over cells):
+//   for each local cell c:
+//     for each gene slab [g0, g0+gl)  (slab = what fits in shared memory beside the accumulators)
+//        TMA bulk copies (UBLKCP) stage e[c, slab] and d[c, slab] into shared memory, completion on an
+//        mbarrier; d is centred in place (b = d - mean, speedboosted.pyx:46-55)
+//        each WARP owns one neighbour row at a time: it streams e[i, slab] from HBM with 128-bit
+//        no-L1-allocate loads (the row is used exactly once by this SM), forms A = f(e_i - e_c) and
+//        accumulates the three one-pass sums  S1 = sum A, S2 = sum A^2, S3 = sum A*b  in 4-way
+//        interleaved fp32 registers, then reduces them with warp shuffles.
+//     finalise: corr = S3 / sqrt((S2 - S1^2/G) * ssb) in fp64, written compactly as out[c, n].
+//
+// The reference's seven fp64 passes over a (genes x m) scratch (speedboosted.pyx:275-346) collapse into
+// one read of every neighbour row: algorithmic HBM traffic  C*(m+2)*G*4 bytes.
+#include "velo_common.cuh"
+
+namespace velo {
+
+constexpr int kThreads = 512;            // 16 warps, 1 CTA / SM (shared memory bound)
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxChunk = 4096;          // neighbours handled per pass (accumulators + indices in smem)
+
+struct CorrParams {
+    const float *e_cm;      // C x ld
+    const float *d_cm;      // nc x ld
+    const float *stats;     // nc x 2 : mean, centred sum of squares
+    const int32_t *ixs;     // nc x ixs_ld, or nullptr (full)
+    float *out;             // nc x out_ld
+    int64_t ld, ixs_ld, out_ld;
+    int64_t G, C, c0, nc, m;
+    int Gs;                 // slab length (multiple of 128), H = ceil(G / Gs)
+    int Mc;                 // neighbour chunk (<= kMaxChunk)
+    float psc;
+};
+
+template <int TR, int RULE>
+__device__ __forceinline__ float transform_diff(float t, float psc)
+{
+    if (TR == VELO_LINEAR) {
+        return t;
+    } else if (TR == VELO_SQRT) {
+        const float a = fabsf(t);
+        const float r = sqrt_approx(a + psc);
+        if (RULE == VELO_RULE_PARTIAL) {
+            // |t| < 1e-16 -> 0 ; t > 0 -> +r ; else -r          (speedboosted.pyx:372-378)
+            return a < 1e-16f ? 0.0f : copysignf(r, t);
+        } else {
+            // t > 0 -> +r ; else (incl. t == 0) -r               (speedboosted.pyx:110-114)
+            return t > 0.0f ? r : -r;
+        }
+    } else {
+        const float a = fabsf(t);
+        const float r = lg2_approx(a + psc) * 0.30102999566398120f;   // log10(x) = log2(x) * log10(2)
+        if (RULE == VELO_RULE_PARTIAL) {
+            return t >= 0.0f ? r : -r;                            // speedboosted.pyx:470-473
+        } else {
+            return t > 0.0f ? r : -r;                             // speedboosted.pyx:195-199
+        }
+    }
+}
+
+struct Acc4 {
+    float s1[4], s2[4], s3[4];
+};
+
+template <int TR, int RULE>
+__device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float4 ec, const float4 b, float psc)
+{
+    const float A0 = transform_diff<TR, RULE>(v.x - ec.x, psc);
+    const float A1 = transform_diff<TR, RULE>(v.y - ec.y, psc);
+    const float A2 = transform_diff<TR, RULE>(v.z - ec.z, psc);
+    const float A3 = transform_diff<TR, RULE>(v.w - ec.w, psc);
+    a.s1[0] += A0; a.s2[0] = fmaf(A0, A0, a.s2[0]); a.s3[0] = fmaf(A0, b.x, a.s3[0]);
+    a.s1[1] += A1; a.s2[1] = fmaf(A1, A1, a.s2[1]); a.s3[1] = fmaf(A1, b.y, a.s3[1]);
+    a.s1[2] += A2; a.s2[2] = fmaf(A2, A2, a.s2[2]); a.s3[2] = fmaf(A2, b.z, a.s3[2]);
+    a.s1[3] += A3; a.s2[3] = fmaf(A3, A3, a.s2[3]); a.s3[3] = fmaf(A3, b.w, a.s3[3]);
+}
+
+template <int TR, int RULE>
+__global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_e = reinterpret_cast<float *>(smem_raw);
+    float *s_b = s_e + p.Gs;
+    float *s_acc = s_b + p.Gs;                                   // 3 x Mc
+    int32_t *s_ix = reinterpret_cast<int32_t *>(s_acc + 3 * p.Mc);   // Mc
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_ix + p.Mc);       // Mc % 2 == 0 -> 8-byte aligned
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int Mc = p.Mc;
+    const int H = static_cast<int>((p.G + p.Gs - 1) / p.Gs);
+    const bool full = p.ixs == nullptr;
+    const double invG = 1.0 / static_cast<double>(p.G);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    for (int64_t r = blockIdx.x; r < p.nc; r += gridDim.x) {
+        const int64_t cg = p.c0 + r;
+        const float mu_b = p.stats[2 * r];
+        const float ssb = p.stats[2 * r + 1];
+        const float *e_row = p.e_cm + cg * p.ld;
+        const float *d_row = p.d_cm + r * p.ld;
+
+        for (int64_t n0 = 0; n0 < p.m; n0 += Mc) {
+            const int mc = static_cast<int>(min(static_cast<int64_t>(Mc), p.m - n0));
+            for (int t = tid; t < mc; t += kThreads) {
+                s_ix[t] = full ? static_cast<int32_t>(n0 + t) : p.ixs[r * p.ixs_ld + n0 + t];
+                s_acc[t] = 0.0f;
+                s_acc[Mc + t] = 0.0f;
+                s_acc[2 * Mc + t] = 0.0f;
+            }
+
+            for (int h = 0; h < H; ++h) {
+                const int64_t g0 = static_cast<int64_t>(h) * p.Gs;
+                const int gl = static_cast<int>(min(static_cast<int64_t>(p.Gs), p.G - g0));
+                const int glp = (gl + 3) & ~3;            // ld % 4 == 0 keeps this inside the row
+                __syncthreads();                          // previous slab fully consumed; s_ix/s_acc init visible
+                if (tid == 0) {
+                    fence_proxy_async_smem();             // generic writes (centering) before async re-fill
+                    mbar_expect_tx(bar, 2u * glp * 4u);
+                    tma_load_1d(s_e, e_row + g0, glp * 4u, bar);
+                    tma_load_1d(s_b, d_row + g0, glp * 4u, bar);
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+                for (int t = tid; t < glp; t += kThreads) s_b[t] -= mu_b;
+                __syncthreads();
+
+                const int nq = gl >> 2;                   // whole float4 groups
+                const float4 *s_e4 = reinterpret_cast<const float4 *>(s_e);
+                const float4 *s_b4 = reinterpret_cast<const float4 *>(s_b);
+                for (int n = warp; n < mc; n += kWarps) {
+                    const int64_t i = s_ix[n];
+                    const float4 *row = reinterpret_cast<const float4 *>(p.e_cm + i * p.ld + g0);
+                    Acc4 a;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a.s1[k] = a.s2[k] = a.s3[k] = 0.0f;
+                    int j = lane;
+                    // 4 independent 128-bit loads in flight per lane
+                    for (; j + 96 < nq; j += 128) {
+                        const float4 v0 = ldg_stream_f4(row + j);
+                        const float4 v1 = ldg_stream_f4(row + j + 32);
+                        const float4 v2 = ldg_stream_f4(row + j + 64);
+                        const float4 v3 = ldg_stream_f4(row + j + 96);
+                        accumulate4<TR, RULE>(a, v0, s_e4[j], s_b4[j], p.psc);
+                        accumulate4<TR, RULE>(a, v1, s_e4[j + 32], s_b4[j + 32], p.psc);
+                        accumulate4<TR, RULE>(a, v2, s_e4[j + 64], s_b4[j + 64], p.psc);
+                        accumulate4<TR, RULE>(a, v3, s_e4[j + 96], s_b4[j + 96], p.psc);
+                    }
+                    for (; j < nq; j += 32) {
+                        const float4 v0 = ldg_stream_f4(row + j);
+                        accumulate4<TR, RULE>(a, v0, s_e4[j], s_b4[j], p.psc);
+                    }
+                    float s1 = (a.s1[0] + a.s1[1]) + (a.s1[2] + a.s1[3]);
+                    float s2 = (a.s2[0] + a.s2[1]) + (a.s2[2] + a.s2[3]);
+                    float s3 = (a.s3[0] + a.s3[1]) + (a.s3[2] + a.s3[3]);
+                    // ragged tail (G % 4 genes of the last slab)
+                    if (lane < (gl & 3)) {
+                        const int k = (nq << 2) + lane;
+                        const float v = __ldg(p.e_cm + i * p.ld + g0 + k);
+                        const float A = transform_diff<TR, RULE>(v - s_e[k], p.psc);
+                        s1 += A;
+                        s2 = fmaf(A, A, s2);
+                        s3 = fmaf(A, s_b[k], s3);
+                    }
+                    s1 = warp_sum(s1);
+                    s2 = warp_sum(s2);
+                    s3 = warp_sum(s3);
+                    if (lane == 0) {                      // slabs are sequential -> deterministic order
+                        s_acc[n] += s1;
+                        s_acc[Mc + n] += s2;
+                        s_acc[2 * Mc + n] += s3;
+                    }
+                }
+            }
+            __syncthreads();
+            // finalise this chunk of neighbours (fp64: a handful of operations per pair)
+            for (int t = tid; t < mc; t += kThreads) {
+                const double S1 = s_acc[t], S2 = s_acc[Mc + t], S3 = s_acc[2 * Mc + t];
+                const double var = S2 - S1 * S1 * invG;
+                const double den = var * static_cast<double>(ssb);
+                // zero variance on either side -> NaN, as 0 * (1/sqrt(0)) in the reference
+                const double corr = (var > 0.0 && ssb > 0.0f) ? S3 / sqrt(den) : __longlong_as_double(0x7ff8000000000000LL);
+                p.out[r * p.out_ld + n0 + t] = static_cast<float>(corr);
+            }
+            __syncthreads();                              // s_acc is re-zeroed by the next chunk
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-cell statistics of the velocity rows (mean, centred sum of squares); one warp per cell
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_stats(const float *__restrict__ d_cm, int64_t ld, int64_t G, int64_t nc,
+                                                    float *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nc) return;
+    const float *row = d_cm + r * ld;
+    double s = 0.0;
+    for (int64_t g = lane; g < G; g += 32) s += static_cast<double>(row[g]);
+    s = warp_sum(s);
+    const double mu = s / static_cast<double>(G);
+    const float muf = static_cast<float>(mu);
+    double q = 0.0;
+    for (int64_t g = lane; g < G; g += 32) {
+        // centre with the fp32 mean: this is the value the correlation kernel subtracts
+        const double b = static_cast<double>(row[g] - muf);
+        q += b * b;
+    }
+    q = warp_sum(q);
+    if (lane == 0) {
+        stats[2 * r] = muf;
+        stats[2 * r + 1] = static_cast<float>(q);
+    }
+}
+
+// rm[(c0+r) * C + i] += out[r, n]
+__global__ void k_scatter_dense(const float *__restrict__ out, int64_t out_ld, const int32_t *__restrict__ ixs,
+                                int64_t ixs_ld, double *__restrict__ rm, int64_t C, int64_t c0, int64_t nc, int64_t m)
+{
+    const int64_t total = nc * m;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = t / m, n = t - r * m;
+        const int64_t i = ixs ? static_cast<int64_t>(ixs[r * ixs_ld + n]) : n;
+        atomicAdd(rm + (c0 + r) * C + i, static_cast<double>(out[r * out_ld + n]));
+    }
+}
+
+// transition probabilities, one warp per cell row
+__global__ void __launch_bounds__(256) k_transition_prob(const float *__restrict__ corr, int64_t ld,
+                                                         const int32_t *__restrict__ ixs, int64_t ixs_ld,
+                                                         float *__restrict__ p, int64_t p_ld, int64_t c0, int64_t nc,
+                                                         int64_t m, float inv_sigma)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nc) return;
+    const float *cr = corr + r * ld;
+    float *pr = p + r * p_ld;
+    const int64_t self = c0 + r;
+    double sum = 0.0;
+    for (int64_t n = lane; n < m; n += 32) {
+        float v = cr[n];
+        const int64_t i = ixs ? static_cast<int64_t>(ixs[r * ixs_ld + n]) : n;
+        if (i == self) v = 0.0f;            // np.fill_diagonal(corrcoef, 0)     analysis.py:1604
+        else if (v != v) v = 1.0f;          // NaN -> 1                           analysis.py:1605-1606
+        const float ex = expf(v * inv_sigma);
+        pr[n] = ex;
+        sum += static_cast<double>(ex);
+    }
+    sum = warp_sum(sum);
+    const float inv = static_cast<float>(1.0 / sum);
+    __syncwarp();
+    for (int64_t n = lane; n < m; n += 32) pr[n] *= inv;
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+template <int TR, int RULE>
+static int launch_corr(const CorrParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    VELO_CUDA_TRY(cudaFuncSetAttribute(k_coldeltacor<TR, RULE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    k_coldeltacor<TR, RULE><<<grid, kThreads, smem, st>>>(p);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+}  // namespace velo
+
+using namespace velo;
+
+extern "C" int velo_dev_cell_stats(const float *d_cm, int64_t ld, int64_t G, int64_t nc, float *stats,
+                                   velo_stream_t stream)
+{
+    VELO_REQUIRE(d_cm && stats && G > 0 && nc >= 0 && ld >= G, "cell_stats: bad arguments");
+    if (nc == 0) return VELO_OK;
+    const int wpb = 8;
+    k_cell_stats<<<static_cast<unsigned>((nc + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(d_cm, ld, G, nc,
+                                                                                                  stats);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+extern "C" int velo_dev_coldeltacor(int transform, int rule, const float *e_cm, const float *d_cm, int64_t ld,
+                                    const float *stats, const int32_t *ixs, int64_t ixs_ld, float *out,
+                                    int64_t out_ld, int64_t G, int64_t C, int64_t c0, int64_t nc, int64_t m,
+                                    double psc, velo_stream_t stream)
+{
+    VELO_REQUIRE(transform >= VELO_LINEAR && transform <= VELO_LOG10, "coldeltacor: unknown transform %d", transform);
+    VELO_REQUIRE(rule == VELO_RULE_FULL || rule == VELO_RULE_PARTIAL, "coldeltacor: unknown rule %d", rule);
+    VELO_REQUIRE(e_cm && d_cm && stats && out, "coldeltacor: null pointer");
+    VELO_REQUIRE(G > 0 && C > 0 && nc >= 0 && c0 >= 0 && c0 + nc <= C && m >= 0, "coldeltacor: bad sizes");
+    VELO_REQUIRE(ld >= G && (ld % 4) == 0, "coldeltacor: ld (%lld) must be >= G and a multiple of 4",
+                 static_cast<long long>(ld));
+    VELO_REQUIRE((reinterpret_cast<uintptr_t>(e_cm) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_cm) & 15) == 0,
+                 "coldeltacor: e_cm/d_cm must be 16-byte aligned");
+    VELO_REQUIRE(ixs != nullptr || m == C, "coldeltacor: full mode (ixs == NULL) requires m == C");
+    VELO_REQUIRE(ixs == nullptr || ixs_ld >= m, "coldeltacor: ixs_ld < m");
+    VELO_REQUIRE(out_ld >= m, "coldeltacor: out_ld < m");
+    VELO_REQUIRE(C < (1LL << 31), "coldeltacor: C must fit int32 indices");
+    if (nc == 0 || m == 0) return VELO_OK;
+
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc != VELO_OK) return rc;
+
+    CorrParams p;
+    p.e_cm = e_cm; p.d_cm = d_cm; p.stats = stats; p.ixs = ixs; p.out = out;
+    p.ld = ld; p.ixs_ld = ixs_ld; p.out_ld = out_ld;
+    p.G = G; p.C = C; p.c0 = c0; p.nc = nc; p.m = m;
+    p.psc = static_cast<float>(psc);
+    // shared-memory plan: [e slab | b slab | 3*Mc accumulators | Mc indices | mbarrier]
+    int Mc = static_cast<int>(m < kMaxChunk ? round_up(m, 2) : kMaxChunk);
+    const int64_t budget = static_cast<int64_t>(dp.smem_optin) - 16LL * Mc - 64;
+    VELO_REQUIRE(budget >= 8 * 128, "coldeltacor: not enough shared memory (%d bytes opt-in)", dp.smem_optin);
+    const int64_t gs_max = (budget / 8) / 128 * 128;           // genes per slab that fit
+    const int64_t H = (G + gs_max - 1) / gs_max;
+    const int64_t Gs = round_up((G + H - 1) / H, 128);         // balanced slabs, 128-gene aligned
+    p.Gs = static_cast<int>(Gs);
+    p.Mc = Mc;
+    const size_t smem = static_cast<size_t>(8 * Gs + 16LL * Mc + 64);
+    const int grid = static_cast<int>(nc < dp.sm_count ? nc : dp.sm_count);
+    cudaStream_t st = as_stream(stream);
+
+#define VELO_DISPATCH(TR)                                                                        \
+    (rule == VELO_RULE_PARTIAL ? launch_corr<TR, VELO_RULE_PARTIAL>(p, grid, smem, st)           \
+                               : launch_corr<TR, VELO_RULE_FULL>(p, grid, smem, st))
+    switch (transform) {
+    case VELO_LINEAR: return VELO_DISPATCH(VELO_LINEAR);
+    case VELO_SQRT: return VELO_DISPATCH(VELO_SQRT);
+    default: return VELO_DISPATCH(VELO_LOG10);
+    }
+#undef VELO_DISPATCH
+}
+
+extern "C" int velo_dev_scatter_dense(const float *out, int64_t out_ld, const int32_t *ixs, int64_t ixs_ld,
+                                      double *rm, int64_t C, int64_t c0, int64_t nc, int64_t m,
+                                      velo_stream_t stream)
+{
+    VELO_REQUIRE(out && rm && C > 0 && nc >= 0 && m >= 0 && c0 >= 0 && c0 + nc <= C, "scatter_dense: bad arguments");
+    VELO_REQUIRE(ixs != nullptr || m == C, "scatter_dense: full mode requires m == C");
+    if (nc == 0 || m == 0) return VELO_OK;
+    const int64_t total = nc * m;
+    const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+    k_scatter_dense<<<grid, 256, 0, as_stream(stream)>>>(out, out_ld, ixs, ixs_ld, rm, C, c0, nc, m);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+extern "C" int velo_dev_transition_prob(const float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld, float *p,
+                                        int64_t p_ld, int64_t c0, int64_t nc, int64_t m, double sigma,
+                                        velo_stream_t stream)
+{
+    VELO_REQUIRE(corr && p && nc >= 0 && m > 0 && ld >= m && p_ld >= m && sigma > 0, "transition_prob: bad arguments");
+    if (nc == 0) return VELO_OK;
+    const int wpb = 8;
+    k_transition_prob<<<static_cast<unsigned>((nc + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(
+        corr, ld, ixs, ixs_ld, p, p_ld, c0, nc, m, static_cast<float>(1.0 / sigma));
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}

@@ -1,0 +1,151 @@
+// Shared helpers for libvelo_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/velo_b200.h"
+
+namespace velo {
+
+// ---- error plumbing ------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define VELO_CUDA_TRY(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::velo::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                              __FILE__, __LINE__);                                           \
+            return _e == cudaErrorMemoryAllocation ? VELO_E_NOMEM : VELO_E_CUDA;             \
+        }                                                                                    \
+    } while (0)
+
+#define VELO_REQUIRE(cond, ...)                                                              \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            ::velo::set_error(__VA_ARGS__);                                                  \
+            return VELO_E_INVALID;                                                           \
+        }                                                                                    \
+    } while (0)
+
+// call after every kernel launch
+#define VELO_LAUNCH_CHECK()                                                                  \
+    do {                                                                                     \
+        ::velo::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
+        VELO_CUDA_TRY(cudaGetLastError());                                                   \
+    } while (0)
+
+struct DeviceProps {
+    int device = -1;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+};
+int get_device_props(DeviceProps *out);   // cached per device; VELO_E_NODEVICE if none
+
+int i64_to_i32_checked(const int64_t *src, int32_t *dst, int64_t n, int64_t bound, int *flag_dev, cudaStream_t st);
+
+static inline cudaStream_t as_stream(velo_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- device-side primitives ------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// mbarrier (shared::cta) -- used as the completion mechanism of TMA bulk copies
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// TMA 1-D bulk copy global -> shared (SASS: UBLKCP). dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// order prior generic-proxy accesses to shared memory before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// streaming 128-bit global load: read-only path, do not allocate in L1 (each neighbour
+// row is consumed exactly once by this SM)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+#endif  // __CUDACC__
+}  // namespace velo
