@@ -106,16 +106,25 @@ def cpu_reference_sample(G, m_full, psc, seconds, steps=1, warmup=0):
     from oracle import velo_oracle as vo
     cores = vo.host_threads()
     kind = "reference" if vo.load_ref_speedboosted() is not None else "port"
-    rate_guess = 0.055e9 * cores                       # pair*gene/s, SURVEY.md section 6
-    m_s = 256
-    C_s = int(max(m_s + 64, min(4096, seconds * rate_guess / (G * m_s))))
-    rng = np.random.default_rng(0)
-    e = rng.gamma(2.0, 1.0, (G, C_s))
-    e[rng.uniform(size=e.shape) < 0.3] = 0.0
-    z = rng.normal(size=(G, C_s))
-    d = np.sqrt(np.abs(z) + psc) * np.sign(z)
-    ixs = np.stack([(c + 1 + rng.choice(C_s - 1, m_s, replace=False)) % C_s for c in range(C_s)]).astype(np.int64)
     fn = vo.ref_coldeltacor if kind == "reference" else vo.coldeltacor
+    rng = np.random.default_rng(0)
+    m_s = 256
+
+    def make(C_s):
+        e = rng.gamma(2.0, 1.0, (G, C_s))
+        e[rng.uniform(size=e.shape) < 0.3] = 0.0
+        z = rng.normal(size=(G, C_s))
+        d = np.sqrt(np.abs(z) + psc) * np.sign(z)
+        ixs = np.stack([(c + 1 + rng.choice(C_s - 1, m_s, replace=False)) % C_s for c in range(C_s)]).astype(np.int64)
+        return e, d, ixs
+
+    # calibrate the host's rate on a ~1 s probe (thread scaling of the reference varies a lot between hosts)
+    e, d, ixs = make(m_s + 64)
+    t0 = time.perf_counter()
+    fn(e, d, ixs, "sqrt", psc, threads=cores)
+    rate = G * (m_s + 64) * m_s / (time.perf_counter() - t0)
+    C_s = int(max(m_s + 64, min(8192, seconds * rate / (G * m_s))))
+    e, d, ixs = make(C_s)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()

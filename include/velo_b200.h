@@ -147,6 +147,56 @@ int velo_dev_transition_prob(const float *corr, int64_t ld, const int32_t *ixs, 
                              float *p, int64_t p_ld, int64_t c0, int64_t nc, int64_t m,
                              double sigma, velo_stream_t stream);
 
+/* ---- gamma fits (K4): replaces the per-gene SciPy loop of velocyto/estimation.py:173-366 ----
+ * S_cm = X (spliced, independent), U_cm = Y (unspliced, dependent), W_cm weights; all C x ld(w)
+ * cell-major fp32.  cell_mask: optional C bytes (the steady_state selection, analysis.py:1159-1162).
+ * mode 0 fit_slope (nnls, estimation.py:173-188,267-279)      -> gamma
+ * mode 1 fit_slope_offset (leastsq/OLS, :244-264,282-297)       -> gamma, offset
+ * mode 2 fit_slope_weighted (bounded (lo,hi), :191-209,300-334) -> gamma [, r2]
+ * mode 3 fit_slope_weighted_offset (box m in [lo,hi], q in [0, 2*sum(yw)/sum(w)], :212-241,337-366)
+ *                                                               -> gamma, offset [, r2]
+ * gamma/offset/r2: G floats (offset, r2 may be NULL); moments: optional 14 x G fp64 sufficient statistics. */
+int velo_dev_fit_gammas(int mode, const float *S_cm, const float *U_cm, int64_t ld,
+                        const float *W_cm, int64_t ldw, const uint8_t *cell_mask,
+                        int64_t G, int64_t C, double lo, double hi,
+                        float *gamma, float *offset, float *r2, double *moments, velo_stream_t stream);
+
+/* ---- elementwise chain (K6): predict_U -> calculate_velocity -> calculate_shift ->
+ * extrapolate_cell_at_t -> velocity transform (analysis.py:1343-1346,1369,1398-1406,1428-1431,1577/1597).
+ * gamma, q (q may be NULL), vel_thr (NULL = no eps threshold): G floats.  assumption 0 = constant_velocity,
+ * 1 = constant_unspliced.  Any of the five C x ld outputs may be NULL. */
+int velo_dev_velocity_chain(const float *S_cm, const float *U_cm, int64_t ld, const float *gamma,
+                            const float *q, const float *vel_thr, int64_t G, int64_t C, int assumption,
+                            double dt_shift, double dt_extrap, int clip, int transform, double psc,
+                            float *Upred, float *vel, float *delta_S, float *S_t, float *d_transformed,
+                            velo_stream_t stream);
+/* thr[g] = eps * max_c (gamma[g]*S[c,g] + q[g])   (analysis.py:1377-1378) */
+int velo_dev_velocity_threshold(const float *S_cm, int64_t ld, const float *gamma, const float *q,
+                                int64_t G, int64_t C, double eps, float *thr, velo_stream_t stream);
+
+/* out = f(dt * delta_S): the `d` argument of the correlation kernel (analysis.py:1577/1594/1597) */
+int velo_dev_delta_transform(const float *delta_S_cm, float *out_cm, int64_t ld, int64_t C, double dt,
+                             int transform, double psc, velo_stream_t stream);
+/* out = S + dt * delta_S, clipped at 0 when clip != 0 (extrapolate_cell_at_t, analysis.py:1429-1431) */
+int velo_dev_extrapolate(const float *S_cm, const float *delta_S_cm, float *out_cm, int64_t ld, int64_t C,
+                         double dt, int clip, velo_stream_t stream);
+/* in place: self pair -> 0, and NaN -> 1 when patch_nan != 0 (analysis.py:1604-1612); *nan_count
+ * (device, may be NULL) is incremented by the number of NaNs replaced */
+int velo_dev_patch_corr(float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld, int64_t c0, int64_t nc,
+                        int64_t m, int patch_nan, unsigned long long *nan_count, velo_stream_t stream);
+/* delta_embedding[r,:] = sum_n (P[r,n] - 1/m) * unit(emb[ixs[r,n]] - emb[c0+r])  (analysis.py:1704-1712);
+ * embedding: C x dims fp64 (first two coordinates used), out: nc x 2 fp64 */
+int velo_dev_embedding_shift(const float *P, int64_t ld, const int32_t *ixs, int64_t ixs_ld,
+                             const double *embedding, int dims, int64_t c0, int64_t nc, int64_t m,
+                             double *out, velo_stream_t stream);
+
+/* ---- kNN smoothing (K5): out[c,:] = sum_p weights[p] * S[indices[p],:], p in [indptr[c], indptr[c+1])
+ * = convolve_by_sparse_weights(data, w) with w in CSR by rows (neighbors.py:416-423, weights from
+ * :385-390); maximum != 0 applies np.maximum(S, Sx) (analysis.py:1017-1019).  fp64 accumulation. */
+int velo_dev_knn_smooth(const int64_t *indptr, const int32_t *indices, const float *weights,
+                        const float *S_cm, float *out_cm, int64_t ld, int64_t G, int64_t C,
+                        int maximum, velo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,484 @@
+"""Drop-in for the hot methods of ``velocyto.analysis.VelocytoLoom`` (velocyto/analysis.py).
+
+Same method names, keyword arguments, attribute names and shapes as the reference for the path
+
+    knn_imputation -> fit_gammas -> predict_U -> calculate_velocity -> calculate_shift ->
+    extrapolate_cell_at_t -> estimate_transition_prob -> calculate_embedding_shift
+
+(the canonical order of doc/tutorial/analysis.rst:108-165).  Method bodies stay Python; all array
+math runs in ``libvelo_b200.so`` on matrices that stay resident in HBM between methods as cell-major
+fp32 (``device.CellMajor``).  The big ``(genes, cells)`` attributes (``Sx_sz``, ``Upred``, ``velocity``
+...) are materialised as float64 NumPy arrays only when they are read, so ``to_hdf5``-style consumers
+and plotting code keep working while a 100k-cell pipeline never round-trips through the host.
+
+What stays on the host, as in the reference: the kNN searches (scikit-learn, analysis.py:1005,1547 --
+SURVEY.md 8f "next"), the neighbour sampler and the randomised control (NumPy / numba RNG streams must
+match the reference's, analysis.py:1552-1566, 2407-2420), and the O(nnz) graph bookkeeping.
+
+Out of scope: loom I/O, filtering, normalisation, PCA/TSNE, plotting, Markov.
+Objects are therefore built from arrays: ``VelocytoLoom(S=..., U=...)``, then the caller sets
+``S_sz``/``U_sz``/``pcs``/``ts`` exactly as the reference's preprocessing methods would have.
+"""
+from __future__ import annotations
+
+import logging
+import warnings
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+from scipy import sparse
+
+from . import _cabi
+from .neighbors import connectivity_to_weights
+
+# (genes, cells) matrices that live on the device once a hot method has produced or consumed them
+_MATRIX_ATTRS = ("S", "U", "S_sz", "U_sz", "Sx", "Ux", "Sx_sz", "Ux_sz", "Upred", "velocity", "delta_S",
+                 "Sx_sz_t", "Sx_t", "delta_S_rndm")
+
+
+class _DeviceBacked:
+    """Descriptor: a ``(genes, cells)`` float64 attribute with a device-resident cell-major twin."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __get__(self, obj, owner=None):
+        if obj is None:
+            return self
+        host = obj.__dict__.setdefault("_host", {})
+        if self.name in host:
+            return host[self.name]
+        devs = obj.__dict__.setdefault("_devs", {})
+        if self.name in devs:
+            host[self.name] = devs[self.name].to_gene_major(np.float64)
+            return host[self.name]
+        raise AttributeError(f"'{type(obj).__name__}' object has no attribute '{self.name}'")
+
+    def __set__(self, obj, value):
+        obj.__dict__.setdefault("_host", {})[self.name] = value
+        obj.__dict__.setdefault("_devs", {}).pop(self.name, None)
+
+    def __delete__(self, obj):
+        obj.__dict__.setdefault("_host", {}).pop(self.name, None)
+        obj.__dict__.setdefault("_devs", {}).pop(self.name, None)
+
+
+def knn_distance_matrix(data: np.ndarray, metric: str = None, k: int = 40, mode: str = "connectivity",
+                        n_jobs: int = 4) -> sparse.csr_matrix:
+    """k nearest neighbours NOT including the point itself (velocyto/neighbors.py:363-376); host, scikit-learn."""
+    from sklearn.neighbors import NearestNeighbors
+    if metric == "correlation":
+        nn = NearestNeighbors(n_neighbors=k, metric="correlation", algorithm="brute", n_jobs=n_jobs)
+    else:
+        nn = NearestNeighbors(n_neighbors=k, n_jobs=n_jobs)
+    nn.fit(data)
+    return nn.kneighbors_graph(X=None, mode=mode)
+
+
+class VelocytoLoom:
+    """The hot-path subset of ``velocyto.analysis.VelocytoLoom`` (velocyto/analysis.py:26-2342)."""
+
+    def __init__(self, S: np.ndarray = None, U: np.ndarray = None, A: np.ndarray = None,
+                 ca: Optional[Dict] = None, ra: Optional[Dict] = None, loom_filepath: str = None) -> None:
+        if loom_filepath is not None:
+            raise NotImplementedError("loom I/O is out of scope (SURVEY.md section 2): pass the S and U count matrices")
+        if S is None or U is None:
+            raise ValueError("S and U (genes x cells) are required")
+        self.S, self.U = np.asarray(S, dtype=np.float64), np.asarray(U, dtype=np.float64)
+        self.A = np.zeros_like(self.S) if A is None else np.asarray(A)
+        self.ca, self.ra = dict(ca or {}), dict(ra or {})
+        self.initial_cell_size = self.S.sum(0)                 # analysis.py:62-63
+        self.initial_Ucell_size = self.U.sum(0)
+
+    # ------------------------------------------------------------------ device residency helpers
+    def _dev(self, name: str):
+        """Cell-major device copy of matrix attribute ``name`` (uploaded on first use)."""
+        from . import device as dev
+        devs = self.__dict__.setdefault("_devs", {})
+        if name not in devs:
+            host = self.__dict__.setdefault("_host", {})
+            if name not in host:
+                raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+            devs[name] = dev.CellMajor.from_gene_major(host[name])
+        return devs[name]
+
+    def _set_dev(self, name: str, cm) -> None:
+        self.__dict__.setdefault("_devs", {})[name] = cm
+        self.__dict__.setdefault("_host", {}).pop(name, None)
+
+    # ------------------------------------------------------------------ knn_imputation (analysis.py:933-1023)
+    def knn_imputation(self, k: int = None, pca_space: float = True, metric: str = "euclidean", diag: float = 1,
+                       n_pca_dims: int = None, maximum: bool = False, size_norm: bool = True,
+                       balanced: bool = False, b_sight: int = None, b_maxl: int = None,
+                       group_constraint: Union[str, np.ndarray] = None, n_jobs: int = 8) -> None:
+        """k-nn smoothing of the data matrix; creates ``knn``, ``knn_smoothing_w``, ``Sx``, ``Ux``, ``Sx_sz``, ``Ux_sz``."""
+        N = self.S.shape[1]
+        if k is None:
+            k = int(N * 0.025)                                                          # analysis.py:983-984
+        if balanced:
+            raise NotImplementedError("balanced=True (BalancedKNN, neighbors.py:186-361: a sequential greedy pass) is "
+                                      "not part of the GPU hot path; build the graph with the reference and call "
+                                      "knn_imputation_precomputed")
+        if group_constraint is not None:
+            raise ValueError("group_constraint is currently supported only if the argument balanced is set to True")
+        space = self.pcs[:, :n_pca_dims] if pca_space else self.S_norm.T                 # analysis.py:989-992
+        self.knn = knn_distance_matrix(space, metric=metric, k=k, mode="distance", n_jobs=n_jobs)
+        connectivity = (self.knn > 0).astype(float)                                      # analysis.py:1006
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            connectivity.setdiag(diag)                                                   # analysis.py:1009
+        self.knn_smoothing_w = connectivity_to_weights(connectivity)                     # analysis.py:1010
+        self._smooth(maximum, size_norm)
+
+    def knn_imputation_precomputed(self, knn_smoothing_w, maximum: bool = False) -> None:
+        """Smoothing with externally computed weights (analysis.py:1025-1053)."""
+        self.knn_smoothing_w = knn_smoothing_w
+        self._smooth(maximum, True)
+
+    def _smooth(self, maximum: bool, size_norm: bool) -> None:
+        from . import device as dev
+        from .neighbors import _csr_rows
+        indptr, indices, weights, wcsr = _csr_rows(self.knn_smoothing_w)
+        assert np.allclose(np.asarray(wcsr.sum(1)).ravel(), 1), "weight matrix need to sum to one over the columns"
+        src_s, src_u = ("S_sz", "U_sz") if size_norm else ("S", "U")                    # analysis.py:1011-1016
+        import torch
+        dv = dev.require_cuda()
+        ip, ix, wt = (torch.from_numpy(indptr).to(dv), torch.from_numpy(indices).to(dv), torch.from_numpy(weights).to(dv))
+        Sx = dev.knn_smooth(ip, ix, wt, self._dev(src_s), maximum)
+        Ux = dev.knn_smooth(ip, ix, wt, self._dev(src_u), maximum)
+        self._set_dev("Sx", Sx)
+        self._set_dev("Ux", Ux)
+        # "a differently named variable for backwards compatibility" -- copies in the reference (analysis.py:1022-1023)
+        self._set_dev("Sx_sz", dev.CellMajor(Sx.t.clone(), Sx.G))
+        self._set_dev("Ux_sz", dev.CellMajor(Ux.t.clone(), Ux.G))
+
+    # ------------------------------------------------------------------ fit_gammas (analysis.py:1120-1260)
+    def fit_gammas(self, steady_state_bool: np.ndarray = None, use_imputed_data: bool = True, use_size_norm: bool = True,
+                   fit_offset: bool = True, fixperc_q: bool = False, weighted: bool = True,
+                   weights: Union[str, np.ndarray] = "maxmin_diag", limit_gamma: bool = False,
+                   maxmin_perc: List[float] = [2, 98], maxmin_weighted_pow: float = 15) -> None:
+        """Fit gamma using spliced and unspliced data; creates ``gammas``, ``q`` (and ``R2`` for weighted fits)."""
+        from . import device as dev
+        if steady_state_bool is not None:                                                # analysis.py:1159-1162
+            self.steady_state = np.asarray(steady_state_bool, dtype=bool)
+        else:
+            self.steady_state = np.ones(self.S.shape[1], dtype=bool)
+        if use_imputed_data:
+            nS, nU = ("Sx_sz", "Ux_sz") if use_size_norm else ("Sx", "Ux")               # analysis.py:1164-1177
+        else:
+            nS, nU = ("S_sz", "U_sz") if use_size_norm else ("S", "U")
+        if fixperc_q or limit_gamma:
+            raise NotImplementedError("fixperc_q / limit_gamma need per-gene percentiles of masked subsets "
+                                      "(estimation.py:199-204, 221-224): not on the GPU path yet")
+        Sd, Ud = self._dev(nS), self._dev(nU)
+        mask = None if self.steady_state.all() else self.steady_state
+        Wd = None
+        if weighted:
+            Wd = self._fit_weights(weights, nS, nU, maxmin_perc, maxmin_weighted_pow)
+        import torch
+        mask_t = None if mask is None else torch.from_numpy(mask.astype(np.uint8))
+        if fit_offset:
+            mode = dev.FIT_SLOPE_WEIGHTED_OFFSET if weighted else dev.FIT_SLOPE_OFFSET
+        else:
+            mode = dev.FIT_SLOPE_WEIGHTED if weighted else dev.FIT_SLOPE
+        lo = 1e-8 if mode == dev.FIT_SLOPE_WEIGHTED_OFFSET else 0.0
+        g, q, r2, _ = dev.fit_gammas(mode, Sd, Ud, Wd, mask_t, lo, 20.0, want_r2=weighted)
+        self._gamma_dev, self._q_dev = torch.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0), q
+        self.gammas = g.cpu().numpy()
+        self.q = q.cpu().numpy() if fit_offset else np.zeros_like(self.gammas)          # analysis.py:1250,1257
+        if weighted:
+            self.R2 = r2.cpu().numpy()
+        self.gammas[~np.isfinite(self.gammas)] = 0                                      # analysis.py:1260
+
+    def _fit_weights(self, weights, nS: str, nU: str, maxmin_perc, maxmin_weighted_pow):
+        """Weight matrix of the least-squares fit (analysis.py:1179-1219) as a device matrix.
+
+        The per-gene percentiles are order statistics over the cell axis (np.percentile, linear
+        interpolation); they are evaluated on the host for now."""
+        from . import device as dev
+        if isinstance(weights, np.ndarray):
+            return dev.CellMajor.from_gene_major(weights)
+        tmpS, tmpU = getattr(self, nS), getattr(self, nU)
+
+        def _denom(M):                                                                   # analysis.py:1197-1199
+            den = np.percentile(M, 99.9, 1)
+            z = den == 0
+            if np.sum(z):
+                den[z] = np.maximum(np.max(M[z, :], 1), 0.001)
+            return den
+
+        if weights == "sum":
+            W = tmpS / np.percentile(tmpS, 99, 1)[:, None] + tmpU / np.percentile(tmpU, 99, 1)[:, None]
+        elif weights == "prod":
+            W = (tmpS / np.percentile(tmpS, 99, 1)[:, None]) * (tmpU / np.percentile(tmpU, 99, 1)[:, None])
+        elif weights == "maxmin_weighted":
+            down, up = np.percentile(tmpS, maxmin_perc, 1)
+            R = np.clip(tmpS, down[:, None], up[:, None])
+            R -= R.min(1)[:, None]
+            R /= R.max(1)[:, None]
+            W = 0.5 * (R ** maxmin_weighted_pow + (1 - R) ** maxmin_weighted_pow)
+        elif weights == "maxmin":
+            down, up = np.percentile(tmpS, maxmin_perc, 1)
+            W = ((tmpS <= down[:, None]) | (tmpS >= up[:, None])).astype(float)
+        elif weights in ("maxmin_diag", "maxmin_double"):
+            Sx, Ux = self.Sx, self.Ux
+            X = Sx / _denom(Sx)[:, None] + Ux / _denom(Ux)[:, None]
+            down, up = np.percentile(X, maxmin_perc, axis=1)
+            W = ((X <= down[:, None]) | (X >= up[:, None])).astype(float)
+            if weights == "maxmin_double":
+                down, up = np.percentile(Sx, maxmin_perc, 1)
+                W += ((Sx <= down[:, None]) | (Sx >= up[:, None])).astype(float)
+        else:
+            raise ValueError(f"unknown weights={weights!r}")
+        return dev.CellMajor.from_gene_major(W)
+
+    # ------------------------------------------------------------------ predict_U .. extrapolate (analysis.py:1321-1439)
+    def _gamma_q(self, which_gamma: str, which_offset: Optional[str]):
+        import torch
+        from . import device as dev
+        dv = dev.require_cuda()
+        g = torch.from_numpy(np.asarray(getattr(self, which_gamma), dtype=np.float32)).to(dv)
+        q = None if which_offset is None else torch.from_numpy(np.asarray(getattr(self, which_offset), dtype=np.float32)).to(dv)
+        return g, q
+
+    def predict_U(self, which_gamma: str = "gammas", which_S: str = "Sx_sz", which_offset: str = "q") -> None:
+        """``Upred = gamma * S (+ q)`` (analysis.py:1321-1346)."""
+        from . import device as dev
+        self.which_S_for_pred = which_S
+        if which_offset is None and (hasattr(self, "q_W") or hasattr(self, "q")):
+            logging.warning("Predicting U without intercept but intercept was previously fit! Set which_offset='q' or 'q_W' ")
+        self._pred_gamma, self._pred_q = self._gamma_q(which_gamma, which_offset)
+        Sd = self._dev(which_S)
+        out = dev.velocity_chain(Sd, Sd, self._pred_gamma, self._pred_q, want=("Upred",))   # U is not read for Upred
+        self._set_dev("Upred", out["Upred"])
+
+    def calculate_velocity(self, kind: str = "residual", eps: float = None) -> None:
+        """``velocity = U_measured - U_predicted`` (analysis.py:1348-1379)."""
+        from . import device as dev
+        if kind != "residual":
+            raise NotImplementedError(f"Velocity calculation kind={kind} is not implemented")
+        if self.which_S_for_pred not in ("Sx_sz", "Sx"):
+            return                                                                       # analysis.py:1373 (no-op, sic)
+        nS = self.which_S_for_pred
+        nU = "Ux_sz" if nS == "Sx_sz" else "Ux"
+        out = dev.velocity_chain(self._dev(nS), self._dev(nU), self._pred_gamma, self._pred_q, eps=eps,
+                                 want=("velocity",))
+        self._velocity_eps = eps
+        self._set_dev("velocity", out["velocity"])
+
+    def calculate_shift(self, assumption: str = "constant_velocity", delta_t: float = 1) -> None:
+        """``delta_S`` under Model I / Model II (analysis.py:1381-1408)."""
+        from . import device as dev
+        if assumption not in ("constant_velocity", "constant_unspliced"):
+            raise NotImplementedError(f"Assumption {assumption} is not implemented")
+        if assumption == "constant_unspliced":
+            g, q = self._gamma_q("gammas", "q")                                          # analysis.py:1403-1406 uses self.gammas/self.q
+            out = dev.velocity_chain(self._dev("Sx_sz"), self._dev("Ux_sz"), g, q, assumption=assumption,
+                                     dt_shift=delta_t, want=("delta_S",))
+        else:
+            nS = self.which_S_for_pred
+            nU = "Ux_sz" if nS == "Sx_sz" else "Ux"
+            out = dev.velocity_chain(self._dev(nS), self._dev(nU), self._pred_gamma, self._pred_q, dt_shift=delta_t,
+                                     eps=getattr(self, "_velocity_eps", None), want=("delta_S",))
+        self._shift = (assumption, float(delta_t))
+        self._set_dev("delta_S", out["delta_S"])
+
+    def extrapolate_cell_at_t(self, delta_t: float = 1, clip: bool = True) -> None:
+        """``Sx_sz_t = clip(Sx_sz + delta_t * delta_S, 0)`` (analysis.py:1410-1439)."""
+        from . import device as dev
+        if self.which_S_for_pred not in ("Sx_sz", "Sx"):
+            return
+        nS = self.which_S_for_pred
+        out = dev.extrapolate(self._dev(nS), self._dev("delta_S"), delta_t, clip)
+        if clip:
+            self.used_delta_t = delta_t                                                  # analysis.py:1432 (set only when clip, sic)
+        self._set_dev("Sx_sz_t" if nS == "Sx_sz" else "Sx_t", out)
+
+    # ------------------------------------------------------------------ estimate_transition_prob (analysis.py:1452-1668)
+    def estimate_transition_prob(self, hidim: str = "Sx_sz", embed: str = "ts", transform: str = "sqrt",
+                                 ndims: int = None, n_sight: int = None, psc: float = None,
+                                 knn_random: bool = True, sampled_fraction: float = 0.3,
+                                 sampling_probs: Tuple[float, float] = (0.5, 0.1), max_dist_embed: float = None,
+                                 n_jobs: int = 4, threads: int = None, calculate_randomized: bool = True,
+                                 random_seed: int = 15071990, **kwargs) -> None:
+        """Correlation of the velocity with the displacement towards each embedding neighbour.
+
+        Creates ``corrcoef`` (+ ``corrcoef_random``), ``embedding``, ``embedding_knn``, ``sampling_ixs``,
+        ``corr_calc``, ``delta_S_rndm`` as the reference does.  ``corrcoef`` is the dense ``(cells, cells)``
+        float64 matrix when it fits comfortably (cells <= ``dense_limit``, default 20000) and is always
+        available in compact form as ``corrcoef_compact`` / ``neigh_ixs`` (cells x m)."""
+        import torch
+        from sklearn.neighbors import NearestNeighbors
+        from . import device as dev
+        dense_limit = kwargs.pop("dense_limit", 20000)
+        for stale in ("_corrcoef_random_dev", "corrcoef_random", "corrcoef_random_compact"):
+            self.__dict__.pop(stale, None)
+        _numba_seed(random_seed)                                                         # analysis.py:1501
+        self.which_hidim = hidim
+        if "n_neighbors" in kwargs:
+            n_neighbors = kwargs.pop("n_neighbors")
+            if len(kwargs) > 0:
+                logging.warning(f"keyword arguments were passed but could not be interpreted {kwargs}")
+        else:
+            n_neighbors = None
+        if n_sight is None and n_neighbors is None:
+            n_neighbors = int(self.S.shape[1] / 5)
+        if (n_sight is not None) and (n_neighbors is not None) and n_neighbors != n_sight:
+            raise ValueError("n_sight and n_neighbors are different names for the same parameter, they cannot be set differently")
+        if n_sight is not None and n_neighbors is None:
+            n_neighbors = n_sight
+        if psc is None:                                                                  # analysis.py:1520-1526
+            psc = 1. if transform in ("log", "logratio") else (1e-10 if transform == "sqrt" else 0)
+        if transform not in ("log", "sqrt", "linear", "logratio"):
+            raise NotImplementedError(f"transform={transform} is not a valid parameter")
+        if transform == "logratio":
+            raise NotImplementedError("transform='logratio' (log2 pre-transform of hidim, analysis.py:1582-1590) is not on the GPU path yet")
+        if "pcs" in hidim:
+            raise NotImplementedError("hidim='pcs' is not on the GPU path; use the expression space (default Sx_sz)")
+        if ndims is not None:
+            raise ValueError(f"ndims was set to {ndims} but hidim != 'pcs'. Set ndims = None for hidim='{hidim}'")
+        if knn_random:
+            np.random.seed(random_seed)                                                  # analysis.py:1529
+        self.corr_calc = "knn_random" if knn_random else "full"
+        e_cm = self._dev(hidim)
+        C, G = e_cm.C, e_cm.G
+        dS = self._dev("delta_S")
+        used_dt = float(self.used_delta_t)
+        tname = {"log": "log10", "sqrt": "sqrt", "linear": "linear"}[transform]
+
+        def transformed(delta_cm):
+            # d = f(hi_dim_t - hi_dim), hi_dim_t = hi_dim + used_delta_t * delta_S   (analysis.py:1538, 1577/1594/1597)
+            return dev.delta_transform(delta_cm, used_dt, tname, psc)
+
+        d_cm = transformed(dS)
+        d_rnd = None
+        if calculate_randomized:                                                         # analysis.py:1539-1542
+            rnd = np.copy(self.delta_S)
+            _permute_rows_nsign(rnd)
+            self.delta_S_rndm = rnd
+            d_rnd = transformed(self._dev("delta_S_rndm"))
+        embedding = getattr(self, embed)
+        self.embedding = embedding
+        nn = NearestNeighbors(n_neighbors=n_neighbors + 1, n_jobs=n_jobs)
+        nn.fit(embedding)
+        self.embedding_knn = nn.kneighbors_graph(mode="connectivity")                   # analysis.py:1547-1549
+        if knn_random:
+            neigh_ixs = self.embedding_knn.indices.reshape((-1, n_neighbors + 1))
+            p = np.linspace(sampling_probs[0], sampling_probs[1], neigh_ixs.shape[1])
+            p = p / p.sum()
+            size = int(sampled_fraction * (n_neighbors + 1))
+            sampling_ixs = np.stack([np.random.choice(neigh_ixs.shape[1], size=(size,), replace=False, p=p)
+                                     for _ in range(neigh_ixs.shape[0])], 0)             # analysis.py:1561-1564
+            self.sampling_ixs = sampling_ixs
+            neigh_ixs = neigh_ixs[np.arange(neigh_ixs.shape[0])[:, None], sampling_ixs]
+            nonzero = neigh_ixs.shape[0] * neigh_ixs.shape[1]
+            self.embedding_knn = sparse.csr_matrix((np.ones(nonzero), neigh_ixs.ravel(),
+                                                    np.arange(0, nonzero + 1, neigh_ixs.shape[1])),
+                                                   shape=(neigh_ixs.shape[0], neigh_ixs.shape[0]))
+            ix = dev.indices_to_device(neigh_ixs, C)
+            self.neigh_ixs = neigh_ixs
+        else:
+            ix = None
+            self.neigh_ixs = None
+        self._ix_dev = ix
+        corr = dev.coldeltacor(e_cm, d_cm, ix, tname, psc)
+        self._finish_corr("corrcoef", corr, ix, C, dense_limit, warn=knn_random)
+        if calculate_randomized:
+            corr_r = dev.coldeltacor(e_cm, d_rnd, ix, tname, psc)
+            self._finish_corr("corrcoef_random", corr_r, ix, C, dense_limit, warn=knn_random)
+
+    def _finish_corr(self, name: str, corr, ix, C: int, dense_limit: int, warn: bool) -> None:
+        """diag -> 0, NaN -> 1 (analysis.py:1604-1612, 1666-1668) on the compact result; dense adapter for small C."""
+        from . import device as dev
+        # np.fill_diagonal(corrcoef, 0); knn_random mode also maps NaN -> 1 with a warning
+        if dev.patch_corr(corr, ix, 0, patch_nan=warn):
+            logging.warning(f"Nans encountered in {name} and corrected to 1s. If not identical cells were present "
+                            "it is probably a small isolated cluster converging after imputation.")
+        setattr(self, "_" + name + "_dev", corr)
+        setattr(self, name + "_compact", corr.cpu().numpy())
+        if C <= dense_limit:
+            setattr(self, name, dev.scatter_dense(corr, ix, C).cpu().numpy())
+        elif hasattr(self, name):
+            delattr(self, name)
+
+    # ------------------------------------------------------------------ calculate_embedding_shift (analysis.py:1670-1733)
+    def calculate_embedding_shift(self, sigma_corr: float = 0.05, expression_scaling: bool = True,
+                                  scaling_penalty: float = 1., dense_limit: int = 20000) -> None:
+        """Transition probabilities (exponential kernel on the correlations, row-normalised over the
+        embedding neighbourhood) and their projection on the embedding.
+
+        ``transition_prob_compact`` (cells x m, aligned with ``neigh_ixs``) always; the reference's dense
+        ``transition_prob`` / ``delta_embedding`` when cells <= ``dense_limit``."""
+        import torch
+        from . import device as dev
+        if self.corr_calc not in ("full", "knn_random"):
+            raise NotImplementedError(f"Weird value self.corr_calc={self.corr_calc}")
+        C = self.embedding.shape[0]
+        ix = self._ix_dev
+        if ix is None:
+            # full mode: the mask is the (n_neighbors + 1)-nn graph of the embedding (analysis.py:1634, 1697)
+            knn = self.embedding_knn.tocsr()
+            m = int(knn.indptr[1] - knn.indptr[0])
+            nb = knn.indices.reshape(C, m)
+            ix_m = dev.indices_to_device(nb, C)
+            self.neigh_ixs = nb
+        else:
+            ix_m = ix
+        names = [("corrcoef", "transition_prob")]
+        if hasattr(self, "_corrcoef_random_dev"):
+            names.append(("corrcoef_random", "transition_prob_random"))
+        for cname, pname in names:
+            corr = getattr(self, "_" + cname + "_dev")
+            if ix is None:
+                corr = torch.gather(corr, 1, ix_m.to(torch.int64))
+            tp = dev.transition_prob(corr.contiguous(), ix_m, sigma_corr)
+            setattr(self, "_" + pname + "_dev", tp)
+            setattr(self, pname + "_compact", tp.cpu().numpy())
+            if C <= dense_limit:
+                setattr(self, pname, dev.scatter_dense(tp, ix_m, C).cpu().numpy())
+        # delta_embedding = sum_j (P_ij - 1/k) * unit(emb_j - emb_i), neighbours only (analysis.py:1704-1712)
+        for cname, pname in names:
+            de = dev.embedding_shift(getattr(self, "_" + pname + "_dev"), ix_m, self.embedding)
+            if expression_scaling:
+                raise NotImplementedError("expression_scaling=True needs two more (genes x cells) sparse products "
+                                          "(analysis.py:1714-1719): SURVEY.md 8f item 1, not built yet; pass "
+                                          "expression_scaling=False")
+            setattr(self, "delta_embedding" if pname == "transition_prob" else "delta_embedding_random", de.cpu().numpy())
+
+
+for _n in _MATRIX_ATTRS:
+    setattr(VelocytoLoom, _n, _DeviceBacked(_n))
+
+
+# --------------------------------------------------------------------------- host RNG helpers (analysis.py:2407-2420)
+def _numba_seed(value: int) -> None:
+    _jit_helpers()[0](value)
+
+
+def _permute_rows_nsign(A: np.ndarray) -> None:
+    _jit_helpers()[1](A)
+
+
+_JIT = None
+
+
+def _jit_helpers():
+    """numba-compiled twins of ``numba_random_seed`` / ``permute_rows_nsign``: the randomised control must
+    consume numba's MT19937 stream exactly as the reference does to be reproducible against it."""
+    global _JIT
+    if _JIT is None:
+        from numba import jit
+
+        @jit(nopython=True)
+        def seed(value):
+            np.random.seed(value)
+
+        @jit(nopython=True)
+        def permute(A):
+            plmi = np.array([+1, -1])
+            for i in range(A.shape[0]):
+                np.random.shuffle(A[i, :])
+                A[i, :] = A[i, :] * np.random.choice(plmi, size=A.shape[1])
+
+        _JIT = (seed, permute)
+    return _JIT

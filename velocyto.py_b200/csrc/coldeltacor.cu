@@ -124,9 +124,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                 const int64_t g0 = static_cast<int64_t>(h) * p.Gs;
                 const int gl = static_cast<int>(min(static_cast<int64_t>(p.Gs), p.G - g0));
                 const int glp = (gl + 3) & ~3;            // ld % 4 == 0 keeps this inside the row
+                fence_proxy_async_smem();                 // every thread: its generic smem accesses (centering writes,
+                                                          // slab reads) are ordered before the async-proxy re-fill
                 __syncthreads();                          // previous slab fully consumed; s_ix/s_acc init visible
                 if (tid == 0) {
-                    fence_proxy_async_smem();             // generic writes (centering) before async re-fill
                     mbar_expect_tx(bar, 2u * glp * 4u);
                     tma_load_1d(s_e, e_row + g0, glp * 4u, bar);
                     tma_load_1d(s_b, d_row + g0, glp * 4u, bar);

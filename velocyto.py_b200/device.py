@@ -176,3 +176,105 @@ def scatter_dense(compact: torch.Tensor, ixs: Optional[torch.Tensor], C: int, c0
     _cabi.call("velo_dev_scatter_dense", compact.data_ptr(), compact.stride(0), 0 if ixs is None else ixs.data_ptr(),
                0 if ixs is None else ixs.stride(0), rm.data_ptr(), C, c0, nc, m, _stream_ptr())
     return rm
+
+
+# --------------------------------------------------------------------------- K4: gamma fits
+FIT_SLOPE, FIT_SLOPE_OFFSET, FIT_SLOPE_WEIGHTED, FIT_SLOPE_WEIGHTED_OFFSET = 0, 1, 2, 3
+
+
+def fit_gammas(mode: int, S_cm: CellMajor, U_cm: CellMajor, W_cm: Optional[CellMajor] = None,
+               cell_mask: Optional[torch.Tensor] = None, lo: float = 0.0, hi: float = 20.0,
+               want_r2: bool = False, want_moments: bool = False):
+    """Batched per-gene fit (estimation.py:173-366).  Returns ``(gamma, offset, r2, moments)`` CUDA tensors
+    (float32 ``(G,)``; ``r2`` / ``moments`` None unless requested)."""
+    G, C, device = S_cm.G, S_cm.C, S_cm.t.device
+    assert U_cm.G == G and U_cm.C == C and U_cm.ld == S_cm.ld
+    gamma = torch.empty(G, dtype=torch.float32, device=device)
+    offset = torch.zeros(G, dtype=torch.float32, device=device)
+    r2 = torch.empty(G, dtype=torch.float32, device=device) if want_r2 else None
+    mom = torch.empty((14, G), dtype=torch.float64, device=device) if want_moments else None
+    if cell_mask is not None:
+        cell_mask = cell_mask.to(device=device, dtype=torch.uint8).contiguous()
+        assert cell_mask.numel() == C
+    if mode >= 2:
+        assert W_cm is not None and W_cm.G == G and W_cm.C == C
+    _cabi.call("velo_dev_fit_gammas", mode, S_cm.ptr, U_cm.ptr, S_cm.ld,
+               0 if W_cm is None else W_cm.ptr, 0 if W_cm is None else W_cm.ld,
+               0 if cell_mask is None else cell_mask.data_ptr(), G, C, float(lo), float(hi),
+               gamma.data_ptr(), offset.data_ptr(), 0 if r2 is None else r2.data_ptr(),
+               0 if mom is None else mom.data_ptr(), _stream_ptr())
+    return gamma, offset, r2, mom
+
+
+# --------------------------------------------------------------------------- K6: elementwise chain
+def velocity_chain(S_cm: CellMajor, U_cm: CellMajor, gamma: torch.Tensor, q: Optional[torch.Tensor] = None,
+                   assumption: str = "constant_velocity", dt_shift: float = 1.0, dt_extrap: float = 1.0,
+                   clip: bool = True, transform: str = "sqrt", psc: float = 1e-10, eps: Optional[float] = None,
+                   want=("Upred", "velocity", "delta_S", "S_t", "d")):
+    """predict_U -> calculate_velocity -> calculate_shift -> extrapolate_cell_at_t -> transform, one pass
+    (analysis.py:1321-1439, 1577/1597).  Returns a dict of CellMajor outputs named in ``want``."""
+    G, C, device = S_cm.G, S_cm.C, S_cm.t.device
+    gamma = gamma.to(device=device, dtype=torch.float32).contiguous()
+    if q is not None:
+        q = q.to(device=device, dtype=torch.float32).contiguous()
+    thr = None
+    if eps:
+        thr = torch.empty(G, dtype=torch.float32, device=device)
+        _cabi.call("velo_dev_velocity_threshold", S_cm.ptr, S_cm.ld, gamma.data_ptr(),
+                   0 if q is None else q.data_ptr(), G, C, float(eps), thr.data_ptr(), _stream_ptr())
+    outs = {k: CellMajor.empty(C, G, device) for k in want}
+    ptr = lambda k: outs[k].ptr if k in outs else 0
+    _cabi.call("velo_dev_velocity_chain", S_cm.ptr, U_cm.ptr, S_cm.ld, gamma.data_ptr(),
+               0 if q is None else q.data_ptr(), 0 if thr is None else thr.data_ptr(), G, C,
+               {"constant_velocity": 0, "constant_unspliced": 1}[assumption], float(dt_shift), float(dt_extrap),
+               int(bool(clip)), _cabi.TRANSFORMS[transform], float(psc),
+               ptr("Upred"), ptr("velocity"), ptr("delta_S"), ptr("S_t"), ptr("d"), _stream_ptr())
+    return outs
+
+
+# --------------------------------------------------------------------------- K5: kNN smoothing
+def knn_smooth(indptr, indices, weights, S_cm: CellMajor, maximum: bool = False) -> CellMajor:
+    """``Sx[c, :] = sum_n w[c, n] * S[idx[c, n], :]`` for a CSR-by-rows weight matrix (neighbors.py:416-423)."""
+    device = S_cm.t.device
+    as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(
+        device=device, dtype=dt).contiguous()
+    indptr, indices, weights = as_t(indptr, torch.int64), as_t(indices, torch.int32), as_t(weights, torch.float32)
+    assert indptr.numel() == S_cm.C + 1
+    out = CellMajor.empty(S_cm.C, S_cm.G, device)
+    _cabi.call("velo_dev_knn_smooth", indptr.data_ptr(), indices.data_ptr(), weights.data_ptr(), S_cm.ptr, out.ptr,
+               S_cm.ld, S_cm.G, S_cm.C, int(bool(maximum)), _stream_ptr())
+    return out
+
+
+def delta_transform(delta_S: CellMajor, dt: float, transform: str, psc: float) -> CellMajor:
+    """``d = f(dt * delta_S)``: the velocity argument of colDeltaCor* (analysis.py:1577/1594/1597)."""
+    out = CellMajor(torch.empty_like(delta_S.t), delta_S.G)
+    _cabi.call("velo_dev_delta_transform", delta_S.ptr, out.ptr, delta_S.ld, delta_S.C, float(dt),
+               _cabi.TRANSFORMS[transform], float(psc), _stream_ptr())
+    return out
+
+
+def extrapolate(S: CellMajor, delta_S: CellMajor, dt: float, clip: bool) -> CellMajor:
+    """``clip(S + dt * delta_S, 0)`` (analysis.py:1429-1431)."""
+    out = CellMajor(torch.empty_like(S.t), S.G)
+    _cabi.call("velo_dev_extrapolate", S.ptr, delta_S.ptr, out.ptr, S.ld, S.C, float(dt), int(bool(clip)), _stream_ptr())
+    return out
+
+
+def patch_corr(corr: torch.Tensor, ixs: Optional[torch.Tensor], c0: int = 0, patch_nan: bool = True) -> int:
+    """In place: self pair -> 0, NaN -> 1 (analysis.py:1604-1612).  Returns the number of NaNs replaced."""
+    cnt = torch.zeros(1, dtype=torch.int64, device=corr.device)
+    nc, m = corr.shape
+    _cabi.call("velo_dev_patch_corr", corr.data_ptr(), corr.stride(0), 0 if ixs is None else ixs.data_ptr(),
+               0 if ixs is None else ixs.stride(0), c0, nc, m, int(bool(patch_nan)), cnt.data_ptr(), _stream_ptr())
+    return int(cnt.item())
+
+
+def embedding_shift(tp: torch.Tensor, ixs: torch.Tensor, embedding, c0: int = 0) -> torch.Tensor:
+    """``delta_embedding`` without expression scaling (analysis.py:1704-1712), ``(nc, 2)`` float64."""
+    emb = torch.as_tensor(np.ascontiguousarray(embedding, dtype=np.float64)).to(tp.device)
+    nc, m = tp.shape
+    out = torch.empty((nc, 2), dtype=torch.float64, device=tp.device)
+    _cabi.call("velo_dev_embedding_shift", tp.data_ptr(), tp.stride(0), ixs.data_ptr(), ixs.stride(0), emb.data_ptr(),
+               emb.shape[1], c0, nc, m, out.data_ptr(), _stream_ptr())
+    return out
