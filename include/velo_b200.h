@@ -161,6 +161,17 @@ int velo_dev_fit_gammas(int mode, const float *S_cm, const float *U_cm, int64_t 
                         int64_t G, int64_t C, double lo, double hi,
                         float *gamma, float *offset, float *r2, double *moments, velo_stream_t stream);
 
+/* np.percentile(rows[g, :], q[j]) ("linear" interpolation) for every row of a gene-major fp32 matrix
+ * (rows_gc: G x C; q_dev: nq percentiles in [0,100], DEVICE array; out: G x nq fp64, device) */
+int velo_dev_row_percentiles(const float *rows_gc, int64_t G, int64_t C, const double *q_dev, int nq,
+                             double *out, velo_stream_t stream);
+/* weight matrix of fit_gammas (analysis.py:1179-1219), cell-major fp32 C x ldw.
+ * kind 0 "maxmin_diag" (default), 1 "maxmin", 2 "maxmin_double", 3 "sum", 4 "prod";
+ * S/U = the matrices being fitted (tmpS/tmpU), Sx/Ux = the smoothed matrices the diag modes use. */
+int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_cm, const float *Sx_cm,
+                         const float *Ux_cm, int64_t ld, int64_t G, int64_t C, double perc_lo,
+                         double perc_hi, float *W_cm, int64_t ldw, velo_stream_t stream);
+
 /* ---- elementwise chain (K6): predict_U -> calculate_velocity -> calculate_shift ->
  * extrapolate_cell_at_t -> velocity transform (analysis.py:1343-1346,1369,1398-1406,1428-1431,1577/1597).
  * gamma, q (q may be NULL), vel_thr (NULL = no eps threshold): G floats.  assumption 0 = constant_velocity,

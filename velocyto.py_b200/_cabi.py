@@ -49,6 +49,8 @@ PROTOTYPES = {
     "velo_dev_transition_prob": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _dbl, _ptr]),
     "velo_dev_fit_gammas": (_int, [_int, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _dbl, _dbl,
                                    _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "velo_dev_row_percentiles": (_int, [_ptr, _i64, _i64, _ptr, _int, _ptr, _ptr]),
+    "velo_dev_fit_weights": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl, _ptr, _i64, _ptr]),
     "velo_dev_velocity_chain": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _int, _dbl, _dbl, _int, _int,
                                        _dbl, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "velo_dev_velocity_threshold": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _i64, _dbl, _ptr, _ptr]),

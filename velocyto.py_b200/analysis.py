@@ -193,43 +193,24 @@ class VelocytoLoom:
     def _fit_weights(self, weights, nS: str, nU: str, maxmin_perc, maxmin_weighted_pow):
         """Weight matrix of the least-squares fit (analysis.py:1179-1219) as a device matrix.
 
-        The per-gene percentiles are order statistics over the cell axis (np.percentile, linear
-        interpolation); they are evaluated on the host for now."""
+        The per-gene percentiles (np.percentile, linear interpolation) are order statistics over the cell
+        axis: they are found by a radix-select kernel on the device (``velo_dev_fit_weights``).  Only the
+        rarely used "maxmin_weighted" mode and user-supplied arrays go through the host."""
         from . import device as dev
         if isinstance(weights, np.ndarray):
             return dev.CellMajor.from_gene_major(weights)
-        tmpS, tmpU = getattr(self, nS), getattr(self, nU)
-
-        def _denom(M):                                                                   # analysis.py:1197-1199
-            den = np.percentile(M, 99.9, 1)
-            z = den == 0
-            if np.sum(z):
-                den[z] = np.maximum(np.max(M[z, :], 1), 0.001)
-            return den
-
-        if weights == "sum":
-            W = tmpS / np.percentile(tmpS, 99, 1)[:, None] + tmpU / np.percentile(tmpU, 99, 1)[:, None]
-        elif weights == "prod":
-            W = (tmpS / np.percentile(tmpS, 99, 1)[:, None]) * (tmpU / np.percentile(tmpU, 99, 1)[:, None])
-        elif weights == "maxmin_weighted":
-            down, up = np.percentile(tmpS, maxmin_perc, 1)
-            R = np.clip(tmpS, down[:, None], up[:, None])
-            R -= R.min(1)[:, None]
-            R /= R.max(1)[:, None]
-            W = 0.5 * (R ** maxmin_weighted_pow + (1 - R) ** maxmin_weighted_pow)
-        elif weights == "maxmin":
-            down, up = np.percentile(tmpS, maxmin_perc, 1)
-            W = ((tmpS <= down[:, None]) | (tmpS >= up[:, None])).astype(float)
-        elif weights in ("maxmin_diag", "maxmin_double"):
-            Sx, Ux = self.Sx, self.Ux
-            X = Sx / _denom(Sx)[:, None] + Ux / _denom(Ux)[:, None]
-            down, up = np.percentile(X, maxmin_perc, axis=1)
-            W = ((X <= down[:, None]) | (X >= up[:, None])).astype(float)
-            if weights == "maxmin_double":
-                down, up = np.percentile(Sx, maxmin_perc, 1)
-                W += ((Sx <= down[:, None]) | (Sx >= up[:, None])).astype(float)
-        else:
+        if weights in dev.WEIGHT_KINDS:
+            diag = weights in ("maxmin_diag", "maxmin_double")
+            return dev.fit_weights(weights, self._dev(nS), self._dev(nU), self._dev("Sx") if diag else None,
+                                   self._dev("Ux") if diag else None, maxmin_perc)
+        if weights != "maxmin_weighted":
             raise ValueError(f"unknown weights={weights!r}")
+        tmpS, tmpU = getattr(self, nS), getattr(self, nU)
+        down, up = np.percentile(tmpS, maxmin_perc, 1)                                   # analysis.py:1186-1192
+        R = np.clip(tmpS, down[:, None], up[:, None])
+        R -= R.min(1)[:, None]
+        R /= R.max(1)[:, None]
+        W = 0.5 * (R ** maxmin_weighted_pow + (1 - R) ** maxmin_weighted_pow)
         return dev.CellMajor.from_gene_major(W)
 
     # ------------------------------------------------------------------ predict_U .. extrapolate (analysis.py:1321-1439)

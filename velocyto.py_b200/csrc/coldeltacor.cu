@@ -140,28 +140,58 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                 const int nq = gl >> 2;                   // whole float4 groups
                 const float4 *s_e4 = reinterpret_cast<const float4 *>(s_e);
                 const float4 *s_b4 = reinterpret_cast<const float4 *>(s_b);
-                for (int n = warp; n < mc; n += kWarps) {
-                    const int64_t i = s_ix[n];
-                    const float4 *row = reinterpret_cast<const float4 *>(p.e_cm + i * p.ld + g0);
+                // Each warp streams whole neighbour rows.  The stream is software-pipelined in registers:
+                // while the 4 x 128-bit loads of group k are being consumed, those of group k+1 -- or of the
+                // first group of the warp's NEXT row -- are already in flight (8 loads = 128 B per lane,
+                // 64 KB per SM outstanding), which is what a random-row HBM gather needs to approach peak.
+                auto load_group = [&](const float4 *row, int base, float4(&v)[4]) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int jj = base + lane + 32 * k;
+                        if (jj < nq) v[k] = ldg_stream_f4(row + jj);
+                    }
+                };
+                auto load_group_full = [&](const float4 *row, int base, float4(&v)[4]) {   // base + 128 <= nq
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = ldg_stream_f4(row + base + lane + 32 * k);
+                };
+                auto row_of = [&](int n) {
+                    return reinterpret_cast<const float4 *>(p.e_cm + static_cast<int64_t>(s_ix[n]) * p.ld + g0);
+                };
+                int n = warp;
+                const float4 *row = nullptr;
+                float4 cur[4];
+                if (n < mc) {
+                    row = row_of(n);
+                    load_group(row, 0, cur);
+                }
+                while (n < mc) {
+                    const int n_next = n + kWarps;
+                    const float4 *row_next = n_next < mc ? row_of(n_next) : nullptr;
                     Acc4 a;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) a.s1[k] = a.s2[k] = a.s3[k] = 0.0f;
-                    int j = lane;
-                    // 4 independent 128-bit loads in flight per lane
-                    for (; j + 96 < nq; j += 128) {
-                        const float4 v0 = ldg_stream_f4(row + j);
-                        const float4 v1 = ldg_stream_f4(row + j + 32);
-                        const float4 v2 = ldg_stream_f4(row + j + 64);
-                        const float4 v3 = ldg_stream_f4(row + j + 96);
-                        accumulate4<TR, RULE>(a, v0, s_e4[j], s_b4[j], p.psc);
-                        accumulate4<TR, RULE>(a, v1, s_e4[j + 32], s_b4[j + 32], p.psc);
-                        accumulate4<TR, RULE>(a, v2, s_e4[j + 64], s_b4[j + 64], p.psc);
-                        accumulate4<TR, RULE>(a, v3, s_e4[j + 96], s_b4[j + 96], p.psc);
+                    for (int base = 0; base < nq; base += 128) {          // warp-uniform trip count
+                        float4 nxt[4];
+                        if (base + 256 <= nq) load_group_full(row, base + 128, nxt);
+                        else if (base + 128 < nq) load_group(row, base + 128, nxt);
+                        else if (row_next) load_group(row_next, 0, nxt);
+                        const int j = base + lane;
+                        if (base + 128 <= nq) {                           // full group: no predicates
+                            accumulate4<TR, RULE>(a, cur[0], s_e4[j], s_b4[j], p.psc);
+                            accumulate4<TR, RULE>(a, cur[1], s_e4[j + 32], s_b4[j + 32], p.psc);
+                            accumulate4<TR, RULE>(a, cur[2], s_e4[j + 64], s_b4[j + 64], p.psc);
+                            accumulate4<TR, RULE>(a, cur[3], s_e4[j + 96], s_b4[j + 96], p.psc);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (j + 32 * k < nq)
+                                    accumulate4<TR, RULE>(a, cur[k], s_e4[j + 32 * k], s_b4[j + 32 * k], p.psc);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
                     }
-                    for (; j < nq; j += 32) {
-                        const float4 v0 = ldg_stream_f4(row + j);
-                        accumulate4<TR, RULE>(a, v0, s_e4[j], s_b4[j], p.psc);
-                    }
+                    const int64_t i = s_ix[n];
                     float s1 = (a.s1[0] + a.s1[1]) + (a.s1[2] + a.s1[3]);
                     float s2 = (a.s2[0] + a.s2[1]) + (a.s2[2] + a.s2[3]);
                     float s3 = (a.s3[0] + a.s3[1]) + (a.s3[2] + a.s3[3]);
@@ -182,6 +212,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                         s_acc[Mc + n] += s2;
                         s_acc[2 * Mc + n] += s3;
                     }
+                    n = n_next;
+                    row = row_next;
                 }
             }
             __syncthreads();

@@ -1,0 +1,247 @@
+// Per-gene order statistics and the weight matrices of fit_gammas (velocyto/analysis.py:1179-1219).
+//
+// The reference builds its least-squares weights from np.percentile along the cell axis (three full
+// partitions per gene for the default "maxmin_diag").  Here a CTA owns one gene row (gene-major fp32 copy
+// of the matrix) and finds the needed order statistics by an 8-bit-per-pass radix select on the
+// order-preserving integer image of the floats (4 histogram passes + one "next larger value" pass;
+// the row stays L2-resident between passes), then applies NumPy's linear interpolation rule.
+#include "velo_common.cuh"
+
+namespace velo {
+
+__device__ __forceinline__ uint32_t f2key(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// block-wide: the k-th smallest (0-based) element of row[0..n) and the (k+1)-th (== k-th if k == n-1)
+__device__ void block_select_pair(const float *__restrict__ row, int64_t n, int64_t k, float *v_lo, float *v_hi,
+                                  unsigned int *hist /*256*/, unsigned long long *scratch /*4*/)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    uint32_t prefix = 0, mask = 0;
+    int64_t rem = k;
+    unsigned int eq_count = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int b = tid; b < 256; b += nt) hist[b] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < n; i += nt) {
+            const uint32_t u = f2key(row[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int64_t cum = 0;
+            int b = 0;
+            for (; b < 256; ++b) {
+                if (cum + hist[b] > rem) break;
+                cum += hist[b];
+            }
+            scratch[0] = static_cast<unsigned long long>(b);
+            scratch[1] = static_cast<unsigned long long>(rem - cum);
+            scratch[2] = hist[b];
+        }
+        __syncthreads();
+        prefix |= static_cast<uint32_t>(scratch[0]) << shift;
+        mask |= 255u << shift;
+        rem = static_cast<int64_t>(scratch[1]);
+        eq_count = static_cast<unsigned int>(scratch[2]);
+        __syncthreads();
+    }
+    const float lo = key2f(prefix);
+    float hi = lo;
+    if (k + 1 < n && rem + 1 >= static_cast<int64_t>(eq_count)) {
+        // the next order statistic is the smallest key strictly above `prefix`
+        uint32_t best = 0xffffffffu;
+        for (int64_t i = tid; i < n; i += nt) {
+            const uint32_t u = f2key(row[i]);
+            if (u > prefix && u < best) best = u;
+        }
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (tid == 0) scratch[3] = 0xffffffffull;
+        __syncthreads();
+        if ((tid & 31) == 0) atomicMin(&scratch[3], static_cast<unsigned long long>(best));
+        __syncthreads();
+        hi = key2f(static_cast<uint32_t>(scratch[3]));
+        __syncthreads();
+    }
+    *v_lo = lo;
+    *v_hi = hi;
+}
+
+// out[g*nq + j] = np.percentile(rows[g, :], q[j]) with the default "linear" method
+__global__ void __launch_bounds__(256) k_row_percentiles(const float *__restrict__ rows, int64_t G, int64_t C,
+                                                         const double *__restrict__ q, int nq, double *__restrict__ out)
+{
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long scratch[4];
+    const int64_t g = blockIdx.x;
+    const float *row = rows + g * C;
+    for (int j = 0; j < nq; ++j) {
+        const double pos = q[j] / 100.0 * static_cast<double>(C - 1);
+        int64_t k = static_cast<int64_t>(floor(pos));
+        if (k < 0) k = 0;
+        if (k > C - 1) k = C - 1;
+        const double t = pos - static_cast<double>(k);
+        float lo, hi;
+        block_select_pair(row, C, k, &lo, &hi, hist, scratch);
+        if (threadIdx.x == 0) {
+            const double a = lo, b = hi;
+            // numpy's _lerp: a + (b-a)*t, evaluated from the right end for t >= 0.5
+            const double diff = b - a;
+            double r = a + diff * t;
+            if (t >= 0.5) r = b - diff * (1.0 - t);
+            if (t == 0.0) r = a;
+            out[g * nq + j] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// den[g] = perc[g]; zero -> max(rowmax, 0.001)      (analysis.py:1197-1199)
+__global__ void __launch_bounds__(256) k_fix_denominators(const float *__restrict__ rows, int64_t G, int64_t C,
+                                                          const double *__restrict__ perc, float *__restrict__ inv_den)
+{
+    __shared__ float smax[8];
+    const int64_t g = blockIdx.x;
+    double den = perc[g];
+    if (den == 0.0) {                                   // uniform per block
+        float mx = -INFINITY;
+        for (int64_t i = threadIdx.x; i < C; i += blockDim.x) mx = fmaxf(mx, rows[g * C + i]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, smax[w]);
+            den = fmax(static_cast<double>(mx), 0.001);
+        }
+    }
+    if (threadIdx.x == 0) inv_den[g] = static_cast<float>(1.0 / den);
+}
+
+// X[c,g] = S[c,g]*a[g] (op 0: + , op 1: *) U[c,g]*b[g]
+__global__ void __launch_bounds__(256) k_scaled_combine(const float *__restrict__ S, const float *__restrict__ U,
+                                                        const float *__restrict__ a, const float *__restrict__ b,
+                                                        float *__restrict__ X, int64_t ld, int64_t G, int64_t C, int op)
+{
+    const int64_t total = C * ld;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t g = t % ld;
+        float v = 0.f;
+        if (g < G) {
+            const float s = S[t] * a[g], u = U[t] * b[g];
+            v = op == 0 ? s + u : s * u;
+        }
+        X[t] = v;
+    }
+}
+
+// W[c,g] (+)= (X[c,g] <= down[g]) | (X[c,g] >= up[g])
+__global__ void __launch_bounds__(256) k_threshold_weights(const float *__restrict__ X, int64_t ld,
+                                                           const double *__restrict__ thr /*G x 2*/,
+                                                           float *__restrict__ W, int64_t ldw, int64_t G, int64_t C,
+                                                           int accumulate)
+{
+    const int64_t total = C * G;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t c = t / G, g = t - c * G;
+        const double x = X[c * ld + g];
+        const float w = (x <= thr[2 * g] || x >= thr[2 * g + 1]) ? 1.f : 0.f;
+        if (accumulate) W[c * ldw + g] += w;
+        else W[c * ldw + g] = w;
+    }
+}
+
+}  // namespace velo
+
+using namespace velo;
+
+extern "C" int velo_dev_row_percentiles(const float *rows_gc, int64_t G, int64_t C, const double *q_dev, int nq,
+                                        double *out, velo_stream_t stream)
+{
+    VELO_REQUIRE(rows_gc && q_dev && out && G > 0 && C > 0 && nq > 0, "row_percentiles: bad arguments");
+    VELO_REQUIRE(G <= 2147483647LL, "row_percentiles: too many rows");
+    k_row_percentiles<<<static_cast<unsigned>(G), 256, 0, as_stream(stream)>>>(rows_gc, G, C, q_dev, nq, out);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+namespace {
+struct Tmp {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit Tmp(cudaStream_t s) : st(s) {}
+    ~Tmp()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t n) { return cudaMallocAsync(&p, n ? n : 16, st); }
+};
+}  // namespace
+
+// kind: 0 maxmin_diag, 1 maxmin, 2 maxmin_double, 3 sum, 4 prod   (analysis.py:1181-1219)
+extern "C" int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_cm, const float *Sx_cm,
+                                    const float *Ux_cm, int64_t ld, int64_t G, int64_t C, double perc_lo,
+                                    double perc_hi, float *W_cm, int64_t ldw, velo_stream_t stream)
+{
+    VELO_REQUIRE(kind >= 0 && kind <= 4, "fit_weights: unknown kind %d", kind);
+    VELO_REQUIRE(S_cm && U_cm && W_cm && G > 0 && C > 0 && ld >= G && ldw >= G, "fit_weights: bad arguments");
+    VELO_REQUIRE((kind != 0 && kind != 2) || (Sx_cm && Ux_cm), "fit_weights: maxmin_diag needs Sx and Ux");
+    cudaStream_t st = as_stream(stream);
+    Tmp rows(st), X(st), perc(st), thr(st), qd(st), invS(st), invU(st);
+    VELO_CUDA_TRY(rows.alloc(static_cast<size_t>(G) * C * 4));
+    VELO_CUDA_TRY(X.alloc(static_cast<size_t>(C) * ld * 4));
+    VELO_CUDA_TRY(perc.alloc(static_cast<size_t>(G) * 8));
+    VELO_CUDA_TRY(thr.alloc(static_cast<size_t>(G) * 2 * 8));
+    VELO_CUDA_TRY(qd.alloc(4 * 8));
+    VELO_CUDA_TRY(invS.alloc(static_cast<size_t>(G) * 4));
+    VELO_CUDA_TRY(invU.alloc(static_cast<size_t>(G) * 4));
+    float *rows_p = static_cast<float *>(rows.p), *X_p = static_cast<float *>(X.p);
+    double *perc_p = static_cast<double *>(perc.p), *thr_p = static_cast<double *>(thr.p), *q_p = static_cast<double *>(qd.p);
+    float *invS_p = static_cast<float *>(invS.p), *invU_p = static_cast<float *>(invU.p);
+    const double qs[4] = {kind <= 2 ? 99.9 : 99.0, perc_lo, perc_hi, 0.0};
+    VELO_CUDA_TRY(cudaMemcpyAsync(q_p, qs, sizeof(qs), cudaMemcpyHostToDevice, st));
+    const int64_t nblk = (C * ld + 255) / 256;
+    const unsigned eg = static_cast<unsigned>(nblk < 148 * 32 ? nblk : 148 * 32);
+    int rc;
+    auto denominators = [&](const float *M, float *inv) -> int {   // 1 / percentile(M, q0, axis=cells), zero-guarded
+        if ((rc = velo_dev_unpack_genemajor(M, ld, G, C, rows_p, 4, stream))) return rc;
+        if ((rc = velo_dev_row_percentiles(rows_p, G, C, q_p, 1, perc_p, stream))) return rc;
+        k_fix_denominators<<<static_cast<unsigned>(G), 256, 0, st>>>(rows_p, G, C, perc_p, inv);
+        VELO_LAUNCH_CHECK();
+        return VELO_OK;
+    };
+    auto thresholds = [&](const float *M, int accumulate) -> int {   // W (+)= (M <= p_lo) | (M >= p_hi)
+        if ((rc = velo_dev_unpack_genemajor(M, ld, G, C, rows_p, 4, stream))) return rc;
+        if ((rc = velo_dev_row_percentiles(rows_p, G, C, q_p + 1, 2, thr_p, stream))) return rc;
+        k_threshold_weights<<<eg, 256, 0, st>>>(M, ld, thr_p, W_cm, ldw, G, C, accumulate);
+        VELO_LAUNCH_CHECK();
+        return VELO_OK;
+    };
+    if (kind == 1) return thresholds(S_cm, 0);                                       // "maxmin"  :1193-1195
+    if (kind == 0 || kind == 2) {                                                    // "maxmin_diag" :1196-1207
+        if ((rc = denominators(Sx_cm, invS_p))) return rc;
+        if ((rc = denominators(Ux_cm, invU_p))) return rc;
+        k_scaled_combine<<<eg, 256, 0, st>>>(Sx_cm, Ux_cm, invS_p, invU_p, X_p, ld, G, C, 0);
+        VELO_LAUNCH_CHECK();
+        if ((rc = thresholds(X_p, 0))) return rc;
+        if (kind == 2) return thresholds(Sx_cm, 1);                                   // "maxmin_double" :1217-1218
+        return VELO_OK;
+    }
+    // "sum" / "prod": S / p99(S) (+|*) U / p99(U)   :1182-1185.  (A zero 99th percentile divides by zero in the
+    // reference; here the denominator falls back to max(row max, 0.001) as in the maxmin_diag branch.)
+    VELO_REQUIRE(ldw == ld, "fit_weights: sum/prod need ldw == ld");
+    if ((rc = denominators(S_cm, invS_p))) return rc;
+    if ((rc = denominators(U_cm, invU_p))) return rc;
+    k_scaled_combine<<<eg, 256, 0, st>>>(S_cm, U_cm, invS_p, invU_p, W_cm, ldw, G, C, kind == 3 ? 0 : 1);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}

@@ -278,3 +278,28 @@ def embedding_shift(tp: torch.Tensor, ixs: torch.Tensor, embedding, c0: int = 0)
     _cabi.call("velo_dev_embedding_shift", tp.data_ptr(), tp.stride(0), ixs.data_ptr(), ixs.stride(0), emb.data_ptr(),
                emb.shape[1], c0, nc, m, out.data_ptr(), _stream_ptr())
     return out
+
+
+# --------------------------------------------------------------------------- fit_gammas weights (analysis.py:1179-1219)
+WEIGHT_KINDS = {"maxmin_diag": 0, "maxmin": 1, "maxmin_double": 2, "sum": 3, "prod": 4}
+
+
+def row_percentiles(M: CellMajor, q) -> torch.Tensor:
+    """``np.percentile(M, q, axis=cells)`` per gene ("linear" interpolation), ``(G, len(q))`` float64 CUDA tensor."""
+    G, C, device = M.G, M.C, M.t.device
+    rows = torch.empty((G, C), dtype=torch.float32, device=device)
+    _cabi.call("velo_dev_unpack_genemajor", M.ptr, M.ld, G, C, rows.data_ptr(), 4, _stream_ptr())
+    qd = torch.as_tensor(np.atleast_1d(np.asarray(q, dtype=np.float64))).to(device)
+    out = torch.empty((G, qd.numel()), dtype=torch.float64, device=device)
+    _cabi.call("velo_dev_row_percentiles", rows.data_ptr(), G, C, qd.data_ptr(), qd.numel(), out.data_ptr(), _stream_ptr())
+    return out
+
+
+def fit_weights(kind: str, S: CellMajor, U: CellMajor, Sx: Optional[CellMajor] = None, Ux: Optional[CellMajor] = None,
+                maxmin_perc=(2, 98)) -> CellMajor:
+    """Weight matrix of the gamma fit built on the device (per-gene radix-select percentiles)."""
+    W = CellMajor.empty(S.C, S.G, S.t.device)
+    _cabi.call("velo_dev_fit_weights", WEIGHT_KINDS[kind], S.ptr, U.ptr, 0 if Sx is None else Sx.ptr,
+               0 if Ux is None else Ux.ptr, S.ld, S.G, S.C, float(maxmin_perc[0]), float(maxmin_perc[1]),
+               W.ptr, W.ld, _stream_ptr())
+    return W
