@@ -107,6 +107,13 @@ int velo_transition_prob_partial(int transform, const void *e, const void *d, in
  * src is a DEVICE pointer; elem_bytes 8 (fp64) or 4 (fp32). */
 int velo_dev_pack_cellmajor(const void *src_gc, int elem_bytes, int64_t G, int64_t C,
                             float *dst_cg, int64_t ld, int64_t g_off, velo_stream_t stream);
+/* As above for fp64 sources, additionally writing the fp32 residuals dst_lo = (float)(x - (double)(float)x)
+ * (same layout) and setting *nonzero_flag (device int, caller-zeroed) to 1 when any residual is non-zero.
+ * The residual matrix lets the correlation kernel reproduce the reference's fp64 sign of e[i]-e[c] for values
+ * that tie in fp32.  dst_lo_cg == NULL behaves like velo_dev_pack_cellmajor. */
+int velo_dev_pack_cellmajor_split(const void *src_gc, int elem_bytes, int64_t G, int64_t C,
+                                  float *dst_cg, float *dst_lo_cg, int *nonzero_flag,
+                                  int64_t ld, int64_t g_off, velo_stream_t stream);
 /* cell-major fp32 -> gene-major fp64/fp32 (inverse of the above, for results that
  * go back to the reference's attribute layout) */
 int velo_dev_unpack_genemajor(const float *src_cg, int64_t ld, int64_t G, int64_t C,
@@ -133,6 +140,15 @@ int velo_dev_coldeltacor(int transform, int rule,
                          float *out, int64_t out_ld,
                          int64_t G, int64_t C, int64_t c0, int64_t nc, int64_t m,
                          double psc, velo_stream_t stream);
+
+/* Same with the optional residual matrix e_lo_cm (C x ld, from velo_dev_pack_cellmajor_split; NULL = none):
+ * exact fp32 ties of non-zero values are resolved with the residuals, as the fp64 reference would see them. */
+int velo_dev_coldeltacor_ex(int transform, int rule,
+                            const float *e_cm, const float *e_lo_cm, const float *d_cm, int64_t ld,
+                            const float *stats, const int32_t *ixs, int64_t ixs_ld,
+                            float *out, int64_t out_ld,
+                            int64_t G, int64_t C, int64_t c0, int64_t nc, int64_t m,
+                            double psc, velo_stream_t stream);
 
 /* rm[(c0 + r) * C + i] += out[r, n]  (dense adapter for small C; fp64 atomics so that
  * duplicated indices accumulate as in the reference, speedboosted.pyx:336) */

@@ -128,6 +128,45 @@ def test_continuous_transforms_on_raw_float64_inputs(oracle, name, psc):
     np.testing.assert_allclose(got, want, rtol=0, atol=5e-7)
 
 
+@pytest.mark.parametrize("name,psc", [("sqrt", 1.0), ("log10", 0.5)])
+def test_discontinuous_transforms_on_raw_float64_inputs(oracle, name, psc):
+    """Raw float64 inputs with the transforms that JUMP at zero difference: the host tier keeps the fp32
+    residuals of e and resolves fp32 ties to the sign the fp64 reference sees, so the 5e-7 bound still holds."""
+    G, C, m = 3000, 300, 64
+    e, d = synth(G, C, 15, name, psc, fp32_exact=False)
+    ixs = rand_ixs(C, m, 16)
+    want = oracle.coldeltacor(e, d, ixs, name, psc)
+    got = _call(name, True, e, d, ixs, psc)
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-7)
+    off = ~np.eye(C, dtype=bool)
+    np.testing.assert_allclose(_call(name, False, e, d, None, psc)[off], oracle.coldeltacor(e, d, None, name, psc)[off],
+                               rtol=0, atol=5e-7)
+
+
+def test_fp32_ties_resolved_like_fp64_reference(oracle):
+    """Adversarial: every cell's value of a gene rounds to the SAME float32 (relative spread 1e-10), so all fp32
+    differences are exactly 0 while the fp64 reference sees definite signs -> +-sqrt(psc) per element."""
+    from velocyto_b200 import device as dev
+    G, C, m, psc = 257, 96, 17, 1.0
+    rng = np.random.default_rng(17)
+    base = rng.gamma(2.0, 1.0, (G, 1)).astype(np.float32).astype(np.float64)
+    e = base * (1.0 + 1e-10 * rng.integers(-50, 50, (G, C)))
+    e[::5] = 0.0                                                   # exact zero rows stay exact ties
+    assert np.all(e.astype(np.float32) == e.astype(np.float32)[:, :1])
+    d = _d(rng.normal(size=(G, C)), "sqrt", psc)
+    ixs = rand_ixs(C, m, 18)
+    want = oracle.coldeltacor(e, d, ixs, "sqrt", psc)
+    got = _call("sqrt", True, e, d, ixs, psc)                      # host tier: residuals kept automatically
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-7, equal_nan=True)
+    e_cm = dev.CellMajor.from_gene_major(e, residual=True)          # device tier
+    assert e_cm.lo is not None
+    ix = dev.indices_to_device(ixs, C)
+    comp = dev.coldeltacor(e_cm, dev.CellMajor.from_gene_major(d), ix, "sqrt", psc).cpu().numpy()
+    np.testing.assert_allclose(comp, want[np.arange(C)[:, None], ixs], rtol=0, atol=5e-7, equal_nan=True)
+    # fp32-representable data carries no residual matrix
+    assert dev.CellMajor.from_gene_major(e.astype(np.float32).astype(np.float64), residual=True).lo is None
+
+
 @pytest.mark.parametrize("G", [30001, 61003, 129, 130])
 def test_ragged_and_multislab_gene_axis(oracle, G):
     """G not a multiple of 4/128, and G large enough for 2 and 3 shared-memory slabs."""

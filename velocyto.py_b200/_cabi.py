@@ -40,11 +40,14 @@ PROTOTYPES = {
     "velo_transition_prob_partial": (_int, [_int, _ptr, _ptr, _int, _ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl]),
     # device tier
     "velo_dev_pack_cellmajor": (_int, [_ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr]),
+    "velo_dev_pack_cellmajor_split": (_int, [_ptr, _int, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _ptr]),
     "velo_dev_unpack_genemajor": (_int, [_ptr, _i64, _i64, _i64, _ptr, _int, _ptr]),
     "velo_dev_i64_to_i32": (_int, [_ptr, _ptr, _i64, _ptr]),
     "velo_dev_cell_stats": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
     "velo_dev_coldeltacor": (_int, [_int, _int, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64,
                                     _i64, _i64, _i64, _i64, _i64, _dbl, _ptr]),
+    "velo_dev_coldeltacor_ex": (_int, [_int, _int, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _i64,
+                                       _i64, _i64, _i64, _i64, _i64, _dbl, _ptr]),
     "velo_dev_scatter_dense": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr]),
     "velo_dev_transition_prob": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _dbl, _ptr]),
     "velo_dev_fit_gammas": (_int, [_int, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _dbl, _dbl,

@@ -57,6 +57,7 @@ class _DeviceBacked:
     def __set__(self, obj, value):
         obj.__dict__.setdefault("_host", {})[self.name] = value
         obj.__dict__.setdefault("_devs", {}).pop(self.name, None)
+        obj.__dict__.setdefault("_fp32_exact", set()).discard(self.name)
 
     def __delete__(self, obj):
         obj.__dict__.setdefault("_host", {}).pop(self.name, None)
@@ -91,20 +92,29 @@ class VelocytoLoom:
         self.initial_Ucell_size = self.U.sum(0)
 
     # ------------------------------------------------------------------ device residency helpers
-    def _dev(self, name: str):
-        """Cell-major device copy of matrix attribute ``name`` (uploaded on first use)."""
+    def _dev(self, name: str, residual: bool = False):
+        """Cell-major device copy of matrix attribute ``name`` (uploaded on first use).
+
+        ``residual=True`` (used for the expression matrix of ``estimate_transition_prob``) re-uploads a float64
+        host array together with its fp32 residuals so that fp32 ties keep the sign the reference sees."""
         from . import device as dev
         devs = self.__dict__.setdefault("_devs", {})
-        if name not in devs:
-            host = self.__dict__.setdefault("_host", {})
+        host = self.__dict__.setdefault("_host", {})
+        need_split = (residual and name in host and getattr(host[name], "dtype", None) == np.float64
+                      and (name not in devs or devs[name].lo is None)
+                      and name not in self.__dict__.setdefault("_fp32_exact", set()))
+        if name not in devs or need_split:
             if name not in host:
                 raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
-            devs[name] = dev.CellMajor.from_gene_major(host[name])
+            devs[name] = dev.CellMajor.from_gene_major(host[name], residual=residual)
+            if residual and devs[name].lo is None:
+                self.__dict__["_fp32_exact"].add(name)
         return devs[name]
 
     def _set_dev(self, name: str, cm) -> None:
         self.__dict__.setdefault("_devs", {})[name] = cm
         self.__dict__.setdefault("_host", {}).pop(name, None)
+        self.__dict__.setdefault("_fp32_exact", set()).discard(name)
 
     # ------------------------------------------------------------------ knn_imputation (analysis.py:933-1023)
     def knn_imputation(self, k: int = None, pca_space: float = True, metric: str = "euclidean", diag: float = 1,
@@ -321,7 +331,7 @@ class VelocytoLoom:
         if knn_random:
             np.random.seed(random_seed)                                                  # analysis.py:1529
         self.corr_calc = "knn_random" if knn_random else "full"
-        e_cm = self._dev(hidim)
+        e_cm = self._dev(hidim, residual=True)
         C, G = e_cm.C, e_cm.G
         dS = self._dev("delta_S")
         used_dt = float(self.used_delta_t)

@@ -6,6 +6,7 @@
 // They stage the inputs to HBM in gene-row chunks, convert them on the device to the
 // cell-major fp32 layout of the kernels, run the same device tier the Python layer uses,
 // and bring the result back.  No host arithmetic on the data path.
+#include <math.h>
 #include <stdarg.h>
 
 #include <mutex>
@@ -85,7 +86,7 @@ struct DevBuf {
 
 // upload a host gene-major matrix into a cell-major fp32 device matrix, gene-row chunk by chunk
 static int upload_cellmajor(const void *host_gc, int elem_bytes, int64_t G, int64_t C, float *dst_cg, int64_t ld,
-                            cudaStream_t st)
+                            cudaStream_t st, float *dst_lo = nullptr, int *nz_flag = nullptr)
 {
     const int64_t row_bytes = C * elem_bytes;
     int64_t chunk_rows = (256LL << 20) / (row_bytes > 0 ? row_bytes : 1);
@@ -98,7 +99,7 @@ static int upload_cellmajor(const void *host_gc, int elem_bytes, int64_t G, int6
         const int64_t rows = (G - g0 < chunk_rows) ? G - g0 : chunk_rows;
         VELO_CUDA_TRY(cudaMemcpyAsync(stage.p, static_cast<const char *>(host_gc) + g0 * row_bytes,
                                       static_cast<size_t>(rows * row_bytes), cudaMemcpyHostToDevice, st));
-        rc = velo_dev_pack_cellmajor(stage.p, elem_bytes, rows, C, dst_cg, ld, g0, st);
+        rc = velo_dev_pack_cellmajor_split(stage.p, elem_bytes, rows, C, dst_cg, dst_lo, nz_flag, ld, g0, st);
         if (rc) return rc;
     }
     return VELO_OK;
@@ -128,7 +129,7 @@ static int host_coldeltacor(int transform, int rule, const void *e, const void *
         ~StreamGuard() { cudaStreamDestroy(s); }
     } guard{st};
 
-    DevBuf e_cm, d_cm, stats, out, ix32, ix64, rm_dev, flag;
+    DevBuf e_cm, d_cm, stats, out, ix32, ix64, rm_dev, flag, e_lo, lo_flag;
     if ((rc = e_cm.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
     if ((rc = d_cm.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
     if ((rc = stats.alloc(static_cast<size_t>(C) * 2 * 4, st))) return rc;
@@ -137,8 +138,26 @@ static int host_coldeltacor(int transform, int rule, const void *e, const void *
         VELO_CUDA_TRY(cudaMemsetAsync(e_cm.p, 0, static_cast<size_t>(C * ld) * 4, st));
         VELO_CUDA_TRY(cudaMemsetAsync(d_cm.p, 0, static_cast<size_t>(C * ld) * 4, st));
     }
-    if ((rc = upload_cellmajor(e, elem_bytes, G, C, e_cm.as<float>(), ld, st))) return rc;
+    // fp64 inputs + a transform that jumps at zero difference (sqrt with psc > 0, log10 with psc != 1): keep the
+    // fp32 residuals of e so that fp32 ties resolve to the sign the fp64 reference sees
+    const double jump = transform == VELO_SQRT ? 2.0 * sqrt(psc > 0 ? psc : 0.0)
+                        : transform == VELO_LOG10 ? 2.0 * fabs(log10(psc > 0 ? psc : 1e-300)) : 0.0;
+    const bool want_lo = elem_bytes == 8 && jump > 1e-4;
+    int lo_nonzero = 0;
+    if (want_lo) {
+        if ((rc = e_lo.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
+        if ((rc = lo_flag.alloc(sizeof(int), st))) return rc;
+        VELO_CUDA_TRY(cudaMemsetAsync(e_lo.p, 0, static_cast<size_t>(C * ld) * 4, st));
+        VELO_CUDA_TRY(cudaMemsetAsync(lo_flag.p, 0, sizeof(int), st));
+    }
+    if ((rc = upload_cellmajor(e, elem_bytes, G, C, e_cm.as<float>(), ld, st, want_lo ? e_lo.as<float>() : nullptr,
+                               want_lo ? lo_flag.as<int>() : nullptr)))
+        return rc;
     if ((rc = upload_cellmajor(d, elem_bytes, G, C, d_cm.as<float>(), ld, st))) return rc;
+    if (want_lo) {
+        VELO_CUDA_TRY(cudaMemcpyAsync(&lo_nonzero, lo_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VELO_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     if (ixs) {
         if ((rc = ix64.alloc(static_cast<size_t>(C * m) * 8, st))) return rc;
         if ((rc = ix32.alloc(static_cast<size_t>(C * m) * 4, st))) return rc;
@@ -152,8 +171,9 @@ static int host_coldeltacor(int transform, int rule, const void *e, const void *
         VELO_REQUIRE(bad == 0, "colDeltaCor: ixs holds an index outside [0, %lld)", static_cast<long long>(C));
     }
     if ((rc = velo_dev_cell_stats(d_cm.as<float>(), ld, G, C, stats.as<float>(), st))) return rc;
-    if ((rc = velo_dev_coldeltacor(transform, rule, e_cm.as<float>(), d_cm.as<float>(), ld, stats.as<float>(),
-                                   ixs ? ix32.as<int32_t>() : nullptr, m, out.as<float>(), m, G, C, 0, C, m, psc, st)))
+    if ((rc = velo_dev_coldeltacor_ex(transform, rule, e_cm.as<float>(), lo_nonzero ? e_lo.as<float>() : nullptr,
+                                      d_cm.as<float>(), ld, stats.as<float>(), ixs ? ix32.as<int32_t>() : nullptr, m,
+                                      out.as<float>(), m, G, C, 0, C, m, psc, st)))
         return rc;
     if (out_compact) {
         if (sigma > 0.0 &&

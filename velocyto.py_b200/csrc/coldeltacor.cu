@@ -25,6 +25,7 @@ constexpr int kMaxChunk = 4096;          // neighbours handled per pass (accumul
 
 struct CorrParams {
     const float *e_cm;      // C x ld
+    const float *e_lo;      // optional C x ld residuals e64 - (double)e32 of fp64-origin data (nullptr = none)
     const float *d_cm;      // nc x ld
     const float *stats;     // nc x 2 : mean, centred sum of squares
     const int32_t *ixs;     // nc x ixs_ld, or nullptr (full)
@@ -66,20 +67,39 @@ struct Acc4 {
     float s1[4], s2[4], s3[4];
 };
 
-template <int TR, int RULE>
-__device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float4 ec, const float4 b, float psc)
+// EXACT: the matrix came from fp64 data and carries fp32 residuals (e64 = e32 + lo).  Two DIFFERENT fp64 values
+// can round to the SAME fp32 value; the reference then still sees a non-zero difference with a definite sign,
+// and for psc > 0 the transforms jump by 2*f(0+) across zero.  Rounding is monotone, so the fp32 difference has
+// the right sign whenever it is non-zero; only exact fp32 ties of non-zero values need the residuals, and those
+// are rare (one global load pair per tie).  lo_i / lo_c point at the residuals of the same four genes.
+template <int TR, int RULE, bool EXACT>
+__device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float4 ec, const float4 b, float psc,
+                                            const float *lo_i, const float *lo_c)
 {
-    const float A0 = transform_diff<TR, RULE>(v.x - ec.x, psc);
-    const float A1 = transform_diff<TR, RULE>(v.y - ec.y, psc);
-    const float A2 = transform_diff<TR, RULE>(v.z - ec.z, psc);
-    const float A3 = transform_diff<TR, RULE>(v.w - ec.w, psc);
+    float t0 = v.x - ec.x, t1 = v.y - ec.y, t2 = v.z - ec.z, t3 = v.w - ec.w;
+    if (EXACT) {
+        const bool tie = ((v.x == ec.x) & (v.x != 0.0f)) | ((v.y == ec.y) & (v.y != 0.0f)) |
+                         ((v.z == ec.z) & (v.z != 0.0f)) | ((v.w == ec.w) & (v.w != 0.0f));
+        if (tie) {
+            const float4 li = __ldg(reinterpret_cast<const float4 *>(lo_i));
+            const float4 lc = __ldg(reinterpret_cast<const float4 *>(lo_c));
+            if (t0 == 0.0f) t0 = li.x - lc.x;
+            if (t1 == 0.0f) t1 = li.y - lc.y;
+            if (t2 == 0.0f) t2 = li.z - lc.z;
+            if (t3 == 0.0f) t3 = li.w - lc.w;
+        }
+    }
+    const float A0 = transform_diff<TR, RULE>(t0, psc);
+    const float A1 = transform_diff<TR, RULE>(t1, psc);
+    const float A2 = transform_diff<TR, RULE>(t2, psc);
+    const float A3 = transform_diff<TR, RULE>(t3, psc);
     a.s1[0] += A0; a.s2[0] = fmaf(A0, A0, a.s2[0]); a.s3[0] = fmaf(A0, b.x, a.s3[0]);
     a.s1[1] += A1; a.s2[1] = fmaf(A1, A1, a.s2[1]); a.s3[1] = fmaf(A1, b.y, a.s3[1]);
     a.s1[2] += A2; a.s2[2] = fmaf(A2, A2, a.s2[2]); a.s3[2] = fmaf(A2, b.z, a.s3[2]);
     a.s1[3] += A3; a.s2[3] = fmaf(A3, A3, a.s2[3]); a.s3[3] = fmaf(A3, b.w, a.s3[3]);
 }
 
-template <int TR, int RULE>
+template <int TR, int RULE, bool EXACT>
 __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -158,6 +178,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                 auto row_of = [&](int n) {
                     return reinterpret_cast<const float4 *>(p.e_cm + static_cast<int64_t>(s_ix[n]) * p.ld + g0);
                 };
+                const ptrdiff_t lo_delta =                                                 // floats, between the two matrices
+                    EXACT ? (reinterpret_cast<intptr_t>(p.e_lo) - reinterpret_cast<intptr_t>(p.e_cm)) / 4 : 0;
+                const float *lo_c_row = EXACT ? p.e_lo + cg * p.ld + g0 : nullptr;
                 int n = warp;
                 const float4 *row = nullptr;
                 float4 cur[4];
@@ -177,16 +200,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                         else if (base + 128 < nq) load_group(row, base + 128, nxt);
                         else if (row_next) load_group(row_next, 0, nxt);
                         const int j = base + lane;
+                        // residual rows (EXACT only): same offsets as the value rows, in the e_lo matrix
+                        const float *lo_i = EXACT ? reinterpret_cast<const float *>(row + j) + lo_delta : nullptr;
+                        const float *lo_c = EXACT ? lo_c_row + 4 * j : nullptr;
                         if (base + 128 <= nq) {                           // full group: no predicates
-                            accumulate4<TR, RULE>(a, cur[0], s_e4[j], s_b4[j], p.psc);
-                            accumulate4<TR, RULE>(a, cur[1], s_e4[j + 32], s_b4[j + 32], p.psc);
-                            accumulate4<TR, RULE>(a, cur[2], s_e4[j + 64], s_b4[j + 64], p.psc);
-                            accumulate4<TR, RULE>(a, cur[3], s_e4[j + 96], s_b4[j + 96], p.psc);
+                            accumulate4<TR, RULE, EXACT>(a, cur[0], s_e4[j], s_b4[j], p.psc, lo_i, lo_c);
+                            accumulate4<TR, RULE, EXACT>(a, cur[1], s_e4[j + 32], s_b4[j + 32], p.psc, lo_i + 128, lo_c + 128);
+                            accumulate4<TR, RULE, EXACT>(a, cur[2], s_e4[j + 64], s_b4[j + 64], p.psc, lo_i + 256, lo_c + 256);
+                            accumulate4<TR, RULE, EXACT>(a, cur[3], s_e4[j + 96], s_b4[j + 96], p.psc, lo_i + 384, lo_c + 384);
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 if (j + 32 * k < nq)
-                                    accumulate4<TR, RULE>(a, cur[k], s_e4[j + 32 * k], s_b4[j + 32 * k], p.psc);
+                                    accumulate4<TR, RULE, EXACT>(a, cur[k], s_e4[j + 32 * k], s_b4[j + 32 * k], p.psc,
+                                                                 lo_i + 128 * k, lo_c + 128 * k);
                         }
 #pragma unroll
                         for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
@@ -199,7 +226,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                     if (lane < (gl & 3)) {
                         const int k = (nq << 2) + lane;
                         const float v = __ldg(p.e_cm + i * p.ld + g0 + k);
-                        const float A = transform_diff<TR, RULE>(v - s_e[k], p.psc);
+                        float t = v - s_e[k];
+                        if (EXACT && t == 0.0f && v != 0.0f)
+                            t = __ldg(p.e_lo + i * p.ld + g0 + k) - __ldg(lo_c_row + k);
+                        const float A = transform_diff<TR, RULE>(t, p.psc);
                         s1 += A;
                         s2 = fmaf(A, A, s2);
                         s3 = fmaf(A, s_b[k], s3);
@@ -303,14 +333,21 @@ __global__ void __launch_bounds__(256) k_transition_prob(const float *__restrict
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
+template <int TR, int RULE, bool EXACT>
+static int launch_corr_impl(const CorrParams &p, int grid, size_t smem, cudaStream_t st)
+{
+    VELO_CUDA_TRY(cudaFuncSetAttribute(k_coldeltacor<TR, RULE, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    k_coldeltacor<TR, RULE, EXACT><<<grid, kThreads, smem, st>>>(p);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
 template <int TR, int RULE>
 static int launch_corr(const CorrParams &p, int grid, size_t smem, cudaStream_t st)
 {
-    VELO_CUDA_TRY(cudaFuncSetAttribute(k_coldeltacor<TR, RULE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    k_coldeltacor<TR, RULE><<<grid, kThreads, smem, st>>>(p);
-    VELO_LAUNCH_CHECK();
-    return VELO_OK;
+    // the linear transform is continuous: ties need no special care
+    if (TR != VELO_LINEAR && p.e_lo) return launch_corr_impl<TR, RULE, true>(p, grid, smem, st);
+    return launch_corr_impl<TR, RULE, false>(p, grid, smem, st);
 }
 
 }  // namespace velo
@@ -334,6 +371,15 @@ extern "C" int velo_dev_coldeltacor(int transform, int rule, const float *e_cm, 
                                     int64_t out_ld, int64_t G, int64_t C, int64_t c0, int64_t nc, int64_t m,
                                     double psc, velo_stream_t stream)
 {
+    return velo_dev_coldeltacor_ex(transform, rule, e_cm, nullptr, d_cm, ld, stats, ixs, ixs_ld, out, out_ld, G, C, c0,
+                                   nc, m, psc, stream);
+}
+
+extern "C" int velo_dev_coldeltacor_ex(int transform, int rule, const float *e_cm, const float *e_lo_cm,
+                                       const float *d_cm, int64_t ld, const float *stats, const int32_t *ixs,
+                                       int64_t ixs_ld, float *out, int64_t out_ld, int64_t G, int64_t C, int64_t c0,
+                                       int64_t nc, int64_t m, double psc, velo_stream_t stream)
+{
     VELO_REQUIRE(transform >= VELO_LINEAR && transform <= VELO_LOG10, "coldeltacor: unknown transform %d", transform);
     VELO_REQUIRE(rule == VELO_RULE_FULL || rule == VELO_RULE_PARTIAL, "coldeltacor: unknown rule %d", rule);
     VELO_REQUIRE(e_cm && d_cm && stats && out, "coldeltacor: null pointer");
@@ -353,7 +399,9 @@ extern "C" int velo_dev_coldeltacor(int transform, int rule, const float *e_cm, 
     if (rc != VELO_OK) return rc;
 
     CorrParams p;
-    p.e_cm = e_cm; p.d_cm = d_cm; p.stats = stats; p.ixs = ixs; p.out = out;
+    VELO_REQUIRE(e_lo_cm == nullptr || (reinterpret_cast<uintptr_t>(e_lo_cm) & 15) == 0,
+                 "coldeltacor: e_lo_cm must be 16-byte aligned");
+    p.e_cm = e_cm; p.e_lo = e_lo_cm; p.d_cm = d_cm; p.stats = stats; p.ixs = ixs; p.out = out;
     p.ld = ld; p.ixs_ld = ixs_ld; p.out_ld = out_ld;
     p.G = G; p.C = C; p.c0 = c0; p.nc = nc; p.m = m;
     p.psc = static_cast<float>(psc);

@@ -4,24 +4,40 @@
 
 namespace velo {
 
-template <typename T>
+// SPLIT: also emit the fp32 residual lo = (float)(x - (double)(float)x) of fp64 sources and raise *nz_flag when
+// any residual is non-zero (i.e. the data is not exactly representable in fp32).
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(256) k_pack_cellmajor(const T *__restrict__ src, int64_t G, int64_t C,
-                                                        float *__restrict__ dst, int64_t ld, int64_t g_off)
+                                                        float *__restrict__ dst, float *__restrict__ dst_lo,
+                                                        int *__restrict__ nz_flag, int64_t ld, int64_t g_off)
 {
     __shared__ float tile[32][33];
+    __shared__ float tile_lo[SPLIT ? 32 : 1][33];
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 32;
     const int64_t g0 = static_cast<int64_t>(blockIdx.y) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    bool nz = false;
 #pragma unroll
     for (int k = 0; k < 32; k += 8) {
         const int64_t g = g0 + ty + k, c = c0 + tx;           // coalesced over cells (source rows)
-        tile[ty + k][tx] = (g < G && c < C) ? static_cast<float>(src[g * C + c]) : 0.0f;
+        const T x = (g < G && c < C) ? src[g * C + c] : T(0);
+        const float hi = static_cast<float>(x);
+        tile[ty + k][tx] = hi;
+        if (SPLIT) {
+            const float lo = static_cast<float>(static_cast<double>(x) - static_cast<double>(hi));
+            tile_lo[ty + k][tx] = lo;
+            nz |= lo != 0.0f;
+        }
     }
+    if (SPLIT && nz) atomicExch(nz_flag, 1);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 32; k += 8) {
         const int64_t c = c0 + ty + k, g = g0 + tx;           // coalesced over genes (destination rows)
-        if (c < C && g < G) dst[c * ld + g_off + g] = tile[tx][ty + k];
+        if (c < C && g < G) {
+            dst[c * ld + g_off + g] = tile[tx][ty + k];
+            if (SPLIT) dst_lo[c * ld + g_off + g] = tile_lo[tx][ty + k];
+        }
     }
 }
 
@@ -76,18 +92,30 @@ using namespace velo;
 extern "C" int velo_dev_pack_cellmajor(const void *src_gc, int elem_bytes, int64_t G, int64_t C, float *dst_cg,
                                        int64_t ld, int64_t g_off, velo_stream_t stream)
 {
+    return velo_dev_pack_cellmajor_split(src_gc, elem_bytes, G, C, dst_cg, nullptr, nullptr, ld, g_off, stream);
+}
+
+extern "C" int velo_dev_pack_cellmajor_split(const void *src_gc, int elem_bytes, int64_t G, int64_t C, float *dst_cg,
+                                             float *dst_lo_cg, int *nonzero_flag, int64_t ld, int64_t g_off,
+                                             velo_stream_t stream)
+{
     VELO_REQUIRE(src_gc && dst_cg && G > 0 && C > 0 && g_off >= 0 && ld >= g_off + G, "pack_cellmajor: bad arguments");
     VELO_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "pack_cellmajor: elem_bytes must be 4 or 8");
+    VELO_REQUIRE(dst_lo_cg == nullptr || (elem_bytes == 8 && nonzero_flag), "pack_cellmajor: residuals need fp64 input and a flag");
     const int64_t gy = (G + 31) / 32;
     VELO_REQUIRE(gy <= 65535, "pack_cellmajor: too many genes per call (%lld); chunk the gene axis",
                  static_cast<long long>(G));
     dim3 grid(static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(gy));
-    if (elem_bytes == 8)
-        k_pack_cellmajor<double><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const double *>(src_gc), G, C,
-                                                                      dst_cg, ld, g_off);
+    cudaStream_t st = as_stream(stream);
+    if (dst_lo_cg)
+        k_pack_cellmajor<double, true><<<grid, 256, 0, st>>>(static_cast<const double *>(src_gc), G, C, dst_cg,
+                                                             dst_lo_cg, nonzero_flag, ld, g_off);
+    else if (elem_bytes == 8)
+        k_pack_cellmajor<double, false><<<grid, 256, 0, st>>>(static_cast<const double *>(src_gc), G, C, dst_cg,
+                                                              nullptr, nullptr, ld, g_off);
     else
-        k_pack_cellmajor<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float *>(src_gc), G, C, dst_cg,
-                                                                     ld, g_off);
+        k_pack_cellmajor<float, false><<<grid, 256, 0, st>>>(static_cast<const float *>(src_gc), G, C, dst_cg, nullptr,
+                                                             nullptr, ld, g_off);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }

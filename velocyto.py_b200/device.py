@@ -36,12 +36,15 @@ def padded_ld(G: int) -> int:
 class CellMajor:
     """``(cells, ld)`` float32 CUDA tensor holding a ``(genes, cells)`` matrix transposed."""
 
-    __slots__ = ("t", "G")
+    __slots__ = ("t", "G", "lo")
 
-    def __init__(self, tensor: torch.Tensor, G: int):
+    def __init__(self, tensor: torch.Tensor, G: int, lo: Optional[torch.Tensor] = None):
         assert tensor.is_cuda and tensor.dtype == torch.float32 and tensor.dim() == 2 and tensor.is_contiguous()
         assert tensor.shape[1] % 4 == 0 and tensor.shape[1] >= G
-        self.t, self.G = tensor, int(G)
+        # lo: optional fp32 residuals (e64 - e32) of fp64-origin data, same layout; lets the correlation kernel
+        # resolve fp32 ties the way the fp64 reference sees them (DESIGN.md section 5)
+        assert lo is None or (lo.shape == tensor.shape and lo.dtype == torch.float32 and lo.is_contiguous())
+        self.t, self.G, self.lo = tensor, int(G), lo
 
     @property
     def C(self) -> int:
@@ -61,11 +64,12 @@ class CellMajor:
         return cls(torch.zeros((C, padded_ld(G)), dtype=torch.float32, device=device), G)
 
     @classmethod
-    def from_gene_major(cls, arr, chunk_bytes: int = 256 << 20) -> "CellMajor":
+    def from_gene_major(cls, arr, chunk_bytes: int = 256 << 20, residual: bool = False) -> "CellMajor":
         """Upload a host ``(genes, cells)`` array (float64/float32; any strides) or a CUDA tensor.
 
         The host copy goes over in gene-row chunks and is transposed/converted on the device
-        (``velo_dev_pack_cellmajor``); nothing is transposed on the host.
+        (``velo_dev_pack_cellmajor``); nothing is transposed on the host.  ``residual=True`` keeps the fp32
+        residuals of float64 data (``.lo``; dropped again when the data turns out to be fp32-representable).
         """
         device = require_cuda()
         if isinstance(arr, torch.Tensor):
@@ -76,7 +80,7 @@ class CellMajor:
             if arr.dtype not in (np.float32, np.float64):
                 arr = arr.astype(np.float64)
             G, C = arr.shape
-            if arr.flags.f_contiguous and not arr.flags.c_contiguous:
+            if arr.flags.f_contiguous and not arr.flags.c_contiguous and not (residual and arr.dtype == np.float64):
                 # physically cell-major already (what scipy's sparse product returns)
                 out = cls.empty(C, G, device)
                 out.t[:, :G].copy_(torch.from_numpy(arr.T).to(device, non_blocking=False))
@@ -85,6 +89,10 @@ class CellMajor:
             src = None
         out = cls.empty(C, G, device)
         esz = 8 if (src.dtype == torch.float64 if src is not None else arr.dtype == np.float64) else 4
+        split = residual and esz == 8
+        if split:
+            out.lo = torch.zeros_like(out.t)
+            flag = torch.zeros(1, dtype=torch.int32, device=device)
         rows_per = max(32, min(G, chunk_bytes // max(1, C * esz)))
         for g0 in range(0, G, rows_per):
             g1 = min(G, g0 + rows_per)
@@ -94,8 +102,14 @@ class CellMajor:
                     blk = blk.to(device)
             else:
                 blk = torch.from_numpy(arr[g0:g1]).to(device)
-            _cabi.call("velo_dev_pack_cellmajor", blk.data_ptr(), esz, g1 - g0, C, out.ptr, out.ld, g0, _stream_ptr())
+            if split:
+                _cabi.call("velo_dev_pack_cellmajor_split", blk.data_ptr(), esz, g1 - g0, C, out.ptr, out.lo.data_ptr(),
+                           flag.data_ptr(), out.ld, g0, _stream_ptr())
+            else:
+                _cabi.call("velo_dev_pack_cellmajor", blk.data_ptr(), esz, g1 - g0, C, out.ptr, out.ld, g0, _stream_ptr())
             del blk
+        if split and int(flag.item()) == 0:
+            out.lo = None                      # exactly representable in fp32: nothing to resolve
         return out
 
     def to_gene_major(self, dtype=np.float64) -> np.ndarray:
@@ -107,7 +121,7 @@ class CellMajor:
         return dst.cpu().numpy()
 
     def rows(self, c0: int, nc: int) -> "CellMajor":
-        return CellMajor(self.t[c0:c0 + nc], self.G)
+        return CellMajor(self.t[c0:c0 + nc], self.G, None if self.lo is None else self.lo[c0:c0 + nc])
 
 
 def indices_to_device(ixs, C: int) -> torch.Tensor:
@@ -149,8 +163,8 @@ def coldeltacor(e_cm: CellMajor, d_cm: CellMajor, ixs: Optional[torch.Tensor], t
         stats = cell_stats(d_cm)
     if out is None:
         out = torch.empty((nc, m), dtype=torch.float32, device=e_cm.t.device)
-    _cabi.call("velo_dev_coldeltacor", tr, rule, e_cm.ptr, d_cm.ptr, e_cm.ld, stats.data_ptr(),
-               0 if ixs is None else ixs.data_ptr(), m, out.data_ptr(), out.stride(0),
+    _cabi.call("velo_dev_coldeltacor_ex", tr, rule, e_cm.ptr, 0 if e_cm.lo is None else e_cm.lo.data_ptr(), d_cm.ptr,
+               e_cm.ld, stats.data_ptr(), 0 if ixs is None else ixs.data_ptr(), m, out.data_ptr(), out.stride(0),
                G, C, c0, nc, m, float(psc), _stream_ptr())
     return out
 
