@@ -22,27 +22,58 @@ struct ChainParams {
 
 __device__ __forceinline__ float signf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
+// grid.x = cell, threads sweep the row in float4 steps: no index division, gamma/q come as (L1-resident) float4
 __global__ void __launch_bounds__(256) k_velocity_chain(const ChainParams p)
 {
+    const int64_t c = blockIdx.x;
     const int64_t G4 = (p.G + 3) >> 2;
-    const int64_t total = p.C * G4;
-    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t c = t / G4, g = (t - c * G4) << 2;
+    const bool vec_ok = (p.G & 3) == 0;                   // per-gene vectors are exactly G long
+    for (int64_t g4 = threadIdx.x; g4 < G4; g4 += blockDim.x) {
+        const int64_t g = g4 << 2;
         const int64_t off = c * p.ld + g;                 // ld % 4 == 0 -> 16-byte aligned
         const float4 s4 = *reinterpret_cast<const float4 *>(p.S + off);
         const float4 u4 = *reinterpret_cast<const float4 *>(p.U + off);
         const float s[4] = {s4.x, s4.y, s4.z, s4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
+        float gam4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f}, thr4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec_ok || g + 3 < p.G) {
+            if (vec_ok) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(p.gamma + g));
+                gam4[0] = t.x; gam4[1] = t.y; gam4[2] = t.z; gam4[3] = t.w;
+                if (p.q) {
+                    const float4 r = __ldg(reinterpret_cast<const float4 *>(p.q + g));
+                    q4[0] = r.x; q4[1] = r.y; q4[2] = r.z; q4[3] = r.w;
+                }
+                if (p.vel_thr) {
+                    const float4 r = __ldg(reinterpret_cast<const float4 *>(p.vel_thr + g));
+                    thr4[0] = r.x; thr4[1] = r.y; thr4[2] = r.z; thr4[3] = r.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    gam4[k] = __ldg(p.gamma + g + k);
+                    if (p.q) q4[k] = __ldg(p.q + g + k);
+                    if (p.vel_thr) thr4[k] = __ldg(p.vel_thr + g + k);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (g + k < p.G) {
+                    gam4[k] = __ldg(p.gamma + g + k);
+                    if (p.q) q4[k] = __ldg(p.q + g + k);
+                    if (p.vel_thr) thr4[k] = __ldg(p.vel_thr + g + k);
+                }
+        }
         float up[4], v[4], ds[4], st[4], dt[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int64_t gg = g + k;
             const bool valid = gg < p.G;
-            const float gam = valid ? p.gamma[gg] : 0.f;
-            const float qq = (valid && p.q) ? p.q[gg] : 0.f;
+            const float gam = gam4[k];
+            const float qq = q4[k];
             up[k] = fmaf(gam, s[k], qq);                                  // analysis.py:1343-1346
             v[k] = u[k] - up[k];                                          // analysis.py:1369
-            if (p.vel_thr && valid && fabsf(v[k]) < p.vel_thr[gg]) v[k] = 0.f;
+            if (p.vel_thr && valid && fabsf(v[k]) < thr4[k]) v[k] = 0.f;
             if (p.assumption == 0) {
                 ds[k] = p.dt_shift * v[k];                                // analysis.py:1399
             } else {                                                      // analysis.py:1403-1406
@@ -262,9 +293,8 @@ extern "C" int velo_dev_velocity_chain(const float *S_cm, const float *U_cm, int
     p.ld = ld; p.G = G; p.C = C;
     p.dt_shift = static_cast<float>(dt_shift); p.dt_extrap = static_cast<float>(dt_extrap);
     p.psc = static_cast<float>(psc); p.assumption = assumption; p.transform = transform; p.clip = clip;
-    const int64_t total = C * ((G + 3) / 4);
-    const int64_t blocks = (total + 255) / 256;
-    k_velocity_chain<<<static_cast<unsigned>(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, as_stream(stream)>>>(p);
+    VELO_REQUIRE(C <= 2147483647LL, "velocity_chain: too many cells");
+    k_velocity_chain<<<static_cast<unsigned>(C), 256, 0, as_stream(stream)>>>(p);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }

@@ -33,27 +33,43 @@ __global__ void __launch_bounds__(128) k_gene_moments(const float *__restrict__ 
     const int64_t c_end = min(C, c_begin + cells_per_part);
     double n = 0, sx = 0, sy = 0, sxx = 0, sxy = 0, syy = 0, nzx = 0, nzy = 0;
     double sw = 0, swx = 0, swy = 0, swxx = 0, swxy = 0, swyy = 0;
-    for (int64_t c = c_begin; c < c_end; ++c) {
-        if (cell_mask && !cell_mask[c]) continue;          // steady_state selection (analysis.py:1159-1162)
-        const double x = static_cast<double>(X[c * ld + g]);
-        const double y = static_cast<double>(Y[c * ld + g]);
-        n += 1.0;
-        sx += x;
-        sy += y;
-        sxx = fma(x, x, sxx);
-        sxy = fma(x, y, sxy);
-        syy = fma(y, y, syy);
-        nzx += (x != 0.0);
-        nzy += (y != 0.0);
-        if (WEIGHTED) {
-            const double w = static_cast<double>(W[c * ldw + g]);
-            const double wx = w * x, wy = w * y;
-            sw += w;
-            swx += wx;
-            swy += wy;
-            swxx = fma(wx, x, swxx);
-            swxy = fma(wx, y, swxy);
-            swyy = fma(wy, y, swyy);
+    // 8 cells per trip: all loads of a trip are issued before the (fp64, loop-carried) accumulation
+    // consumes them, so each warp keeps 16-24 independent 128-byte lines in flight
+    constexpr int U = 8;
+    for (int64_t cb = c_begin; cb < c_end; cb += U) {
+        float xs[U], ys[U], ws[U];
+        bool on[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t c = cb + u;
+            on[u] = c < c_end && (!cell_mask || cell_mask[c]);   // steady_state selection (analysis.py:1159-1162)
+            xs[u] = on[u] ? X[c * ld + g] : 0.f;
+            ys[u] = on[u] ? Y[c * ld + g] : 0.f;
+            ws[u] = (WEIGHTED && on[u]) ? W[c * ldw + g] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!on[u]) continue;
+            const double x = static_cast<double>(xs[u]);
+            const double y = static_cast<double>(ys[u]);
+            n += 1.0;
+            sx += x;
+            sy += y;
+            sxx = fma(x, x, sxx);
+            sxy = fma(x, y, sxy);
+            syy = fma(y, y, syy);
+            nzx += (x != 0.0);
+            nzy += (y != 0.0);
+            if (WEIGHTED) {
+                const double w = static_cast<double>(ws[u]);
+                const double wx = w * x, wy = w * y;
+                sw += w;
+                swx += wx;
+                swy += wy;
+                swxx = fma(wx, x, swxx);
+                swxy = fma(wx, y, swxy);
+                swyy = fma(wy, y, swyy);
+            }
         }
     }
     double *out = partials + (part * kMom) * G + g;        // [part][moment][gene] -> coalesced

@@ -51,6 +51,10 @@ int get_device_props(DeviceProps *out);   // cached per device; VELO_E_NODEVICE 
 
 int i64_to_i32_checked(const int64_t *src, int32_t *dst, int64_t n, int64_t bound, int *flag_dev, cudaStream_t st);
 
+int coldeltacor_full_tiled(int transform, const float *e_cm, const float *d_cm, int64_t ld, const float *stats,
+                           float *out, int64_t out_ld, int64_t G, int64_t C, int64_t c0, int64_t nc, double psc,
+                           cudaStream_t st);
+
 static inline cudaStream_t as_stream(velo_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
