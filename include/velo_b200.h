@@ -207,6 +207,14 @@ int velo_dev_delta_transform(const float *delta_S_cm, float *out_cm, int64_t ld,
 /* out = S + dt * delta_S, clipped at 0 when clip != 0 (extrapolate_cell_at_t, analysis.py:1429-1431) */
 int velo_dev_extrapolate(const float *S_cm, const float *delta_S_cm, float *out_cm, int64_t ld, int64_t C,
                          double dt, int clip, velo_stream_t stream);
+/* transform="logratio" operands (analysis.py:1582-1583): which 0: out = log2(S + psc);
+ * which 1: out = log2(|S + dt*delta_S| + psc) - log2(S + psc) */
+int velo_dev_logratio(const float *S_cm, const float *delta_S_cm, float *out_cm, int64_t ld, int64_t C,
+                      double dt, double psc, int which, velo_stream_t stream);
+/* expression scaling of calculate_embedding_shift (analysis.py:1714-1719): scale[c] =
+ * clip( sum_g delta_S[c,g]*estim[c,g] / sqrt(sum_g estim[c,g]^2) / penalty, 0, 1 ), fp64 (device, C values) */
+int velo_dev_row_cosine_scale(const float *delta_S_cm, const float *estim_cm, int64_t ld, int64_t G, int64_t C,
+                              double penalty, double *scale, velo_stream_t stream);
 /* in place: self pair -> 0, and NaN -> 1 when patch_nan != 0 (analysis.py:1604-1612); *nan_count
  * (device, may be NULL) is incremented by the number of NaNs replaced */
 int velo_dev_patch_corr(float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld, int64_t c0, int64_t nc,

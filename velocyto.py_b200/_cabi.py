@@ -59,6 +59,8 @@ PROTOTYPES = {
     "velo_dev_velocity_threshold": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _i64, _dbl, _ptr, _ptr]),
     "velo_dev_delta_transform": (_int, [_ptr, _ptr, _i64, _i64, _dbl, _int, _dbl, _ptr]),
     "velo_dev_extrapolate": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _dbl, _int, _ptr]),
+    "velo_dev_logratio": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _dbl, _dbl, _int, _ptr]),
+    "velo_dev_row_cosine_scale": (_int, [_ptr, _ptr, _i64, _i64, _i64, _dbl, _ptr, _ptr]),
     "velo_dev_patch_corr": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int, _ptr, _ptr]),
     "velo_dev_embedding_shift": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _int, _i64, _i64, _i64, _ptr, _ptr]),
     "velo_dev_knn_smooth": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr]),

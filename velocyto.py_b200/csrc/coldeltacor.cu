@@ -64,8 +64,8 @@ __device__ __forceinline__ float transform_diff(float t, float psc)
     }
 }
 
-struct Acc4 {
-    float s1[4], s2[4], s3[4];
+struct Acc4 {                // 4-way interleaved partial sums, kept as two fp32x2 pairs each
+    float2 s1[2], s2[2], s3[2];
 };
 
 // EXACT: the matrix came from fp64 data and carries fp32 residuals (e64 = e32 + lo).  Two DIFFERENT fp64 values
@@ -77,7 +77,9 @@ template <int TR, int RULE, bool EXACT>
 __device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float4 ec, const float4 b, float psc,
                                             const float *lo_i, const float *lo_c)
 {
-    float t0 = v.x - ec.x, t1 = v.y - ec.y, t2 = v.z - ec.z, t3 = v.w - ec.w;
+    const float2 t01 = sub2(make_float2(v.x, v.y), make_float2(ec.x, ec.y));
+    const float2 t23 = sub2(make_float2(v.z, v.w), make_float2(ec.z, ec.w));
+    float t0 = t01.x, t1 = t01.y, t2 = t23.x, t3 = t23.y;
     if (EXACT) {
         const bool tie = ((v.x == ec.x) & (v.x != 0.0f)) | ((v.y == ec.y) & (v.y != 0.0f)) |
                          ((v.z == ec.z) & (v.z != 0.0f)) | ((v.w == ec.w) & (v.w != 0.0f));
@@ -90,14 +92,11 @@ __device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float
             if (t3 == 0.0f) t3 = li.w - lc.w;
         }
     }
-    const float A0 = transform_diff<TR, RULE>(t0, psc);
-    const float A1 = transform_diff<TR, RULE>(t1, psc);
-    const float A2 = transform_diff<TR, RULE>(t2, psc);
-    const float A3 = transform_diff<TR, RULE>(t3, psc);
-    a.s1[0] += A0; a.s2[0] = fmaf(A0, A0, a.s2[0]); a.s3[0] = fmaf(A0, b.x, a.s3[0]);
-    a.s1[1] += A1; a.s2[1] = fmaf(A1, A1, a.s2[1]); a.s3[1] = fmaf(A1, b.y, a.s3[1]);
-    a.s1[2] += A2; a.s2[2] = fmaf(A2, A2, a.s2[2]); a.s3[2] = fmaf(A2, b.z, a.s3[2]);
-    a.s1[3] += A3; a.s2[3] = fmaf(A3, A3, a.s2[3]); a.s3[3] = fmaf(A3, b.w, a.s3[3]);
+    const float2 A01 = make_float2(transform_diff<TR, RULE>(t0, psc), transform_diff<TR, RULE>(t1, psc));
+    const float2 A23 = make_float2(transform_diff<TR, RULE>(t2, psc), transform_diff<TR, RULE>(t3, psc));
+    // packed accumulation: three FADD2/FFMA2 per element pair instead of six scalar operations
+    a.s1[0] = add2(a.s1[0], A01); a.s2[0] = fma2(A01, A01, a.s2[0]); a.s3[0] = fma2(A01, make_float2(b.x, b.y), a.s3[0]);
+    a.s1[1] = add2(a.s1[1], A23); a.s2[1] = fma2(A23, A23, a.s2[1]); a.s3[1] = fma2(A23, make_float2(b.z, b.w), a.s3[1]);
 }
 
 template <int TR, int RULE, bool EXACT>
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                     const float4 *row_next = n_next < mc ? row_of(n_next) : nullptr;
                     Acc4 a;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) a.s1[k] = a.s2[k] = a.s3[k] = 0.0f;
+                    for (int k = 0; k < 2; ++k) a.s1[k] = a.s2[k] = a.s3[k] = make_float2(0.0f, 0.0f);
                     for (int base = 0; base < nq; base += 128) {          // warp-uniform trip count
                         float4 nxt[4];
                         if (base + 256 <= nq) load_group_full(row, base + 128, nxt);
@@ -248,9 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                         for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
                     }
                     const int64_t i = s_ix[n];
-                    float s1 = (a.s1[0] + a.s1[1]) + (a.s1[2] + a.s1[3]);
-                    float s2 = (a.s2[0] + a.s2[1]) + (a.s2[2] + a.s2[3]);
-                    float s3 = (a.s3[0] + a.s3[1]) + (a.s3[2] + a.s3[3]);
+                    float s1 = (a.s1[0].x + a.s1[0].y) + (a.s1[1].x + a.s1[1].y);
+                    float s2 = (a.s2[0].x + a.s2[0].y) + (a.s2[1].x + a.s2[1].y);
+                    float s3 = (a.s3[0].x + a.s3[0].y) + (a.s3[1].x + a.s3[1].y);
                     // ragged tail (G % 4 genes of the last slab)
                     if (lane < (gl & 3)) {
                         const int k = (nq << 2) + lane;

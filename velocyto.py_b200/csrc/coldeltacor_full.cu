@@ -22,16 +22,17 @@ struct FullParams {
     float psc;
 };
 
-// A for the FULL zero rule, given u = e_c - e_i (note the order).  sqrt: t > 0 ? r : -r with t = -u, i.e.
-// A = -copysign(r, u) (u == +0 -> A = -r, exactly the reference's t == 0 branch, speedboosted.pyx:110-114);
-// log10 likewise (pyx:195-199).
+// -A for the FULL zero rule, given u = e_c - e_i (note the order; u == x - x is +0).  The reference has
+// A = t > 0 ? r : -r with t = -u (speedboosted.pyx:110-114, 195-199), r = sqrt(|t|+psc) or log10(|t|+psc) -- r may be
+// NEGATIVE for log10 with psc < 1 -- hence -A = (u < 0) ? -r : r = r with its sign bit flipped by the sign bit of u:
+// one LOP3, and u == +0 gives -A = r, i.e. A = -r, exactly the reference's t == 0 branch.
 template <int TR>
 __device__ __forceinline__ float full_transform_neg(float u, float psc)   // returns -A
 {
     if (TR == VELO_LINEAR) return u;
     const float a = fabsf(u);
     const float r = TR == VELO_SQRT ? sqrt_approx(a + psc) : lg2_approx(a + psc) * 0.30102999566398120f;
-    return copysignf(r, u);
+    return __int_as_float(__float_as_int(r) ^ (__float_as_int(u) & 0x80000000));
 }
 
 template <int TR>

@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(256) k_knn_smooth(const int64_t *__restrict__ 
     *reinterpret_cast<float4 *>(out + c * ld + g) = r;
 }
 
-// out = f(dt * dS) (mode 0..2 = VELO_LINEAR/SQRT/LOG10, analysis.py:1577/1594/1597) or, mode 3,
-// out = clip?(S + dt * dS) (extrapolate_cell_at_t, analysis.py:1429-1431)
+// out = f(dt * dS) (mode 0..2 = VELO_LINEAR/SQRT/LOG10, analysis.py:1577/1594/1597); mode 3: out = clip?(S + dt * dS)
+// (extrapolate_cell_at_t, analysis.py:1429-1431); modes 4/5: the "logratio" pair log2(S + psc) and
+// log2(|S + dt*dS| + psc) - log2(S + psc) (analysis.py:1582-1583).  Pad columns: S = dS = 0 -> mode 4 writes
+// log2(psc) there, which no kernel reads (all sums stop at G).
 __global__ void __launch_bounds__(256) k_delta_ops(const float *__restrict__ S, const float *__restrict__ dS,
                                                    float *__restrict__ out, int64_t n4, float dt, float psc, int mode,
                                                    int clip)
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) k_delta_ops(const float *__restrict__ S, 
         const float4 d4 = reinterpret_cast<const float4 *>(dS)[t];
         float d[4] = {d4.x, d4.y, d4.z, d4.w}, r[4];
         float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (mode == 3) s4 = reinterpret_cast<const float4 *>(S)[t];
+        if (mode >= 3) s4 = reinterpret_cast<const float4 *>(S)[t];
         const float s[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -166,10 +168,12 @@ __global__ void __launch_bounds__(256) k_delta_ops(const float *__restrict__ S, 
             if (mode == VELO_SQRT) r[k] = sqrtf(fabsf(step) + psc) * signf(step);
             else if (mode == VELO_LOG10) r[k] = log10f(fabsf(step) + psc) * signf(step);
             else if (mode == VELO_LINEAR) r[k] = step;
-            else {
+            else if (mode == 3) {
                 r[k] = s[k] + step;
                 if (clip) r[k] = fmaxf(r[k], 0.f);
-            }
+            } else if (mode == 4) r[k] = log2f(s[k] + psc);                                   // analysis.py:1582
+            else r[k] = log2f(fabsf(s[k] + step) + psc) - log2f(s[k] + psc);                  // analysis.py:1583
+        }
         }
         reinterpret_cast<float4 *>(out)[t] = make_float4(r[0], r[1], r[2], r[3]);
     }
@@ -320,6 +324,54 @@ extern "C" int velo_dev_knn_smooth(const int64_t *indptr, const int32_t *indices
     VELO_REQUIRE(gy <= 65535, "knn_smooth: too many genes");
     dim3 grid(static_cast<unsigned>(C), static_cast<unsigned>(gy));
     k_knn_smooth<<<grid, 256, 0, as_stream(stream)>>>(indptr, indices, weights, S_cm, out_cm, ld, G, maximum);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+extern "C" int velo_dev_logratio(const float *S_cm, const float *delta_S_cm, float *out_cm, int64_t ld, int64_t C,
+                                 double dt, double psc, int which, velo_stream_t stream)
+{
+    VELO_REQUIRE(S_cm && out_cm && ld > 0 && ld % 4 == 0 && C > 0 && (which == 0 || which == 1), "logratio: bad arguments");
+    VELO_REQUIRE(which == 0 || delta_S_cm, "logratio: the delta needs delta_S");
+    const int64_t n4 = C * ld / 4, blocks = (n4 + 255) / 256;
+    k_delta_ops<<<static_cast<unsigned>(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, as_stream(stream)>>>(
+        S_cm, which == 0 ? S_cm : delta_S_cm, out_cm, n4, static_cast<float>(dt), static_cast<float>(psc), 4 + which, 0);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+// cos_proj[c] = sum_g a[c,g]*b[c,g] / sqrt(sum_g b[c,g]^2), clipped to [0,1] after / penalty  (analysis.py:1718-1719)
+namespace velo {
+__global__ void __launch_bounds__(256) k_row_cosine_scale(const float *__restrict__ a, const float *__restrict__ b,
+                                                          int64_t ld, int64_t G, int64_t C, double penalty,
+                                                          double *__restrict__ scale)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double dot = 0.0, nn = 0.0;
+    for (int64_t g = lane; g < G; g += 32) {
+        const double x = a[c * ld + g], y = b[c * ld + g];
+        dot = fma(x, y, dot);
+        nn = fma(y, y, nn);
+    }
+    dot = warp_sum(dot);
+    nn = warp_sum(nn);
+    if (lane == 0) {
+        double v = dot / sqrt(nn) / penalty;              // 0/0 -> NaN propagates like np.clip(nan)
+        if (v < 0.0) v = 0.0;
+        if (v > 1.0) v = 1.0;
+        scale[c] = v;
+    }
+}
+}  // namespace velo
+
+extern "C" int velo_dev_row_cosine_scale(const float *delta_S_cm, const float *estim_cm, int64_t ld, int64_t G, int64_t C,
+                                         double penalty, double *scale, velo_stream_t stream)
+{
+    VELO_REQUIRE(delta_S_cm && estim_cm && scale && G > 0 && C > 0 && ld >= G && penalty > 0, "row_cosine_scale: bad arguments");
+    velo::k_row_cosine_scale<<<static_cast<unsigned>((C + 7) / 8), 256, 0, as_stream(stream)>>>(delta_S_cm, estim_cm, ld, G, C,
+                                                                                                penalty, scale);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }

@@ -20,63 +20,81 @@ namespace velo {
 constexpr int kMom = 14;   // moments per gene
 // index: 0 n, 1 Sx, 2 Sy, 3 Sxx, 4 Sxy, 5 Syy, 6 nnzx, 7 nnzy, 8 Sw, 9 Swx, 10 Swy, 11 Swxx, 12 Swxy, 13 Swyy
 
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(128) k_gene_moments(const float *__restrict__ X, const float *__restrict__ Y,
+// thread = GP adjacent genes (one 128-/64-bit load per matrix and cell), block = 256 threads = 1024 (512) genes
+// = 4 KB (2 KB) contiguous per cell row -- whole DRAM pages instead of 512-byte fragments; 4 cells per trip are
+// loaded before the fp64 accumulation consumes them.  GP = 4 unweighted (8 moments), 2 weighted (14 moments).
+template <int GP> struct VecOf;
+template <> struct VecOf<4> { using type = float4; };
+template <> struct VecOf<2> { using type = float2; };
+
+template <bool WEIGHTED, int GP>
+__global__ void __launch_bounds__(256) k_gene_moments(const float *__restrict__ X, const float *__restrict__ Y,
                                                       const float *__restrict__ W, int64_t ld, int64_t ldw,
                                                       const uint8_t *__restrict__ cell_mask, int64_t G, int64_t C,
                                                       int64_t cells_per_part, double *__restrict__ partials)
 {
-    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    using V = typename VecOf<GP>::type;
+    constexpr int NM = WEIGHTED ? kMom : 8;
+    const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * GP;
     const int64_t part = blockIdx.y;
-    if (g >= G) return;
+    if (g >= G) return;                                    // ld % 4 == 0: a started group is inside the row
     const int64_t c_begin = part * cells_per_part;
     const int64_t c_end = min(C, c_begin + cells_per_part);
-    double n = 0, sx = 0, sy = 0, sxx = 0, sxy = 0, syy = 0, nzx = 0, nzy = 0;
-    double sw = 0, swx = 0, swy = 0, swxx = 0, swxy = 0, swyy = 0;
-    // 8 cells per trip: all loads of a trip are issued before the (fp64, loop-carried) accumulation
-    // consumes them, so each warp keeps 16-24 independent 128-byte lines in flight
-    constexpr int U = 8;
+    double m[NM][GP];
+#pragma unroll
+    for (int k = 0; k < NM; ++k)
+#pragma unroll
+        for (int j = 0; j < GP; ++j) m[k][j] = 0.0;
+    constexpr int U = 4;
     for (int64_t cb = c_begin; cb < c_end; cb += U) {
-        float xs[U], ys[U], ws[U];
+        V xs[U], ys[U], ws[U];
         bool on[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t c = cb + u;
             on[u] = c < c_end && (!cell_mask || cell_mask[c]);   // steady_state selection (analysis.py:1159-1162)
-            xs[u] = on[u] ? X[c * ld + g] : 0.f;
-            ys[u] = on[u] ? Y[c * ld + g] : 0.f;
-            ws[u] = (WEIGHTED && on[u]) ? W[c * ldw + g] : 0.f;
+            if (on[u]) {
+                xs[u] = __ldg(reinterpret_cast<const V *>(X + c * ld + g));
+                ys[u] = __ldg(reinterpret_cast<const V *>(Y + c * ld + g));
+                if (WEIGHTED) ws[u] = __ldg(reinterpret_cast<const V *>(W + c * ldw + g));
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!on[u]) continue;
-            const double x = static_cast<double>(xs[u]);
-            const double y = static_cast<double>(ys[u]);
-            n += 1.0;
-            sx += x;
-            sy += y;
-            sxx = fma(x, x, sxx);
-            sxy = fma(x, y, sxy);
-            syy = fma(y, y, syy);
-            nzx += (x != 0.0);
-            nzy += (y != 0.0);
-            if (WEIGHTED) {
-                const double w = static_cast<double>(ws[u]);
-                const double wx = w * x, wy = w * y;
-                sw += w;
-                swx += wx;
-                swy += wy;
-                swxx = fma(wx, x, swxx);
-                swxy = fma(wx, y, swxy);
-                swyy = fma(wy, y, swyy);
+            const float *xv = reinterpret_cast<const float *>(&xs[u]);
+            const float *yv = reinterpret_cast<const float *>(&ys[u]);
+            const float *wv = reinterpret_cast<const float *>(&ws[u]);
+#pragma unroll
+            for (int j = 0; j < GP; ++j) {
+                const double x = static_cast<double>(xv[j]), y = static_cast<double>(yv[j]);
+                m[0][j] += 1.0;
+                m[1][j] += x;
+                m[2][j] += y;
+                m[3][j] = fma(x, x, m[3][j]);
+                m[4][j] = fma(x, y, m[4][j]);
+                m[5][j] = fma(y, y, m[5][j]);
+                m[6][j] += (x != 0.0);
+                m[7][j] += (y != 0.0);
+                if (WEIGHTED) {
+                    const double w = static_cast<double>(wv[j]);
+                    const double wx = w * x, wy = w * y;
+                    m[NM - 6][j] += w;
+                    m[NM - 5][j] += wx;
+                    m[NM - 4][j] += wy;
+                    m[NM - 3][j] = fma(wx, x, m[NM - 3][j]);
+                    m[NM - 2][j] = fma(wx, y, m[NM - 2][j]);
+                    m[NM - 1][j] = fma(wy, y, m[NM - 1][j]);
+                }
             }
         }
     }
-    double *out = partials + (part * kMom) * G + g;        // [part][moment][gene] -> coalesced
-    out[0 * G] = n;   out[1 * G] = sx;  out[2 * G] = sy;  out[3 * G] = sxx;
-    out[4 * G] = sxy; out[5 * G] = syy; out[6 * G] = nzx; out[7 * G] = nzy;
-    out[8 * G] = sw;  out[9 * G] = swx; out[10 * G] = swy; out[11 * G] = swxx;
-    out[12 * G] = swxy; out[13 * G] = swyy;
+    double *out = partials + (part * kMom) * G + g;        // [part][moment][gene]
+#pragma unroll
+    for (int k = 0; k < kMom; ++k)
+#pragma unroll
+        for (int j = 0; j < GP; ++j)
+            if (g + j < G) out[k * G + j] = k < NM ? m[k < NM ? k : 0][j] : 0.0;
 }
 
 struct FitOpts {
@@ -195,10 +213,14 @@ extern "C" int velo_dev_fit_gammas(int mode, const float *S_cm, const float *U_c
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc) return rc;
-    const int threads = 128;
+    VELO_REQUIRE(ld % 4 == 0 && (!weighted || ldw % 4 == 0), "fit_gammas: ld must be a multiple of 4");
+    const int threads = 128;                                   // finalize kernel: thread = gene
     const int64_t gblocks = (G + threads - 1) / threads;
+    const int mthreads = 256;                                  // moments kernel: thread = 4 (2 if weighted) genes
+    const int gp = weighted ? 2 : 4;
+    const int64_t mblocks = ((G + gp - 1) / gp + mthreads - 1) / mthreads;
     // enough cell-partitions to fill the machine a few times over, at least ~256 cells each
-    int64_t parts = (static_cast<int64_t>(dp.sm_count) * 8 + gblocks - 1) / gblocks;
+    int64_t parts = (static_cast<int64_t>(dp.sm_count) * 4 + mblocks - 1) / mblocks;
     if (parts > (C + 255) / 256) parts = (C + 255) / 256;
     if (parts < 1) parts = 1;
     if (parts > 65535) parts = 65535;
@@ -207,11 +229,11 @@ extern "C" int velo_dev_fit_gammas(int mode, const float *S_cm, const float *U_c
     double *partials = nullptr;
     VELO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&partials),
                                   static_cast<size_t>(parts) * kMom * G * sizeof(double), st));
-    dim3 grid(static_cast<unsigned>(gblocks), static_cast<unsigned>(parts));
+    dim3 grid(static_cast<unsigned>(mblocks), static_cast<unsigned>(parts));
     if (weighted)
-        k_gene_moments<true><<<grid, threads, 0, st>>>(S_cm, U_cm, W_cm, ld, ldw, cell_mask, G, C, cpp, partials);
+        k_gene_moments<true, 2><<<grid, mthreads, 0, st>>>(S_cm, U_cm, W_cm, ld, ldw, cell_mask, G, C, cpp, partials);
     else
-        k_gene_moments<false><<<grid, threads, 0, st>>>(S_cm, U_cm, nullptr, ld, 0, cell_mask, G, C, cpp, partials);
+        k_gene_moments<false, 4><<<grid, mthreads, 0, st>>>(S_cm, U_cm, nullptr, ld, 0, cell_mask, G, C, cpp, partials);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e1 = cudaGetLastError();
     FitOpts opt{mode, lo, hi};

@@ -61,7 +61,10 @@ class CellMajor:
     @classmethod
     def empty(cls, C: int, G: int, device: Optional[torch.device] = None) -> "CellMajor":
         device = device or require_cuda()
-        return cls(torch.zeros((C, padded_ld(G)), dtype=torch.float32, device=device), G)
+        t = torch.empty((C, padded_ld(G)), dtype=torch.float32, device=device)
+        if t.shape[1] != G:
+            t[:, G:].zero_()                   # only the pad columns need defined values
+        return cls(t, G)
 
     @classmethod
     def from_gene_major(cls, arr, chunk_bytes: int = 256 << 20, residual: bool = False) -> "CellMajor":
