@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--psc", type=float, default=1.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-local", action="store_true", help="skip the secondary embedding-local neighbour workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of one CPU sample")
     return ap.parse_args()
 
@@ -255,6 +256,39 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel}
 
+    # ---------------- secondary workload: embedding-local neighbourhoods (what real kNN graphs look like) ----------------
+    local = None
+    if not args.no_local and world == 1:
+        # cells ordered along the embedding (a ring), neighbours = m of the 10/3*m nearest cells (sampled_fraction 0.3):
+        # neighbouring cells share most of their candidate rows, and the kernel's sorted sweep lets CTAs that run
+        # side by side reuse those rows in L2 -> the algorithmic-bytes figure can exceed the HBM roofline.
+        win = min(C - 1, int(round(m / 0.3)))
+        gen = torch.Generator(device="cuda").manual_seed(99)
+        ix_local = torch.empty_like(ix_loc)
+        for r0 in range(0, core.nc, 2048):
+            n = min(2048, core.nc - r0)
+            pick = torch.rand((n, win), device="cuda", generator=gen).topk(m, dim=1).indices          # m distinct of win
+            off = pick - win // 2
+            off = off + (off >= 0).to(off.dtype)                                                      # skip self
+            ix_local[r0:r0 + n] = ((torch.arange(core.c0 + r0, core.c0 + r0 + n, device="cuda")[:, None] + off) % C).to(torch.int32)
+            del pick, off
+        for _ in range(2):
+            core.run(e_loc, d_loc, ix_local)
+        torch.cuda.synchronize()
+        evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
+        ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ta.record()
+        for k in range(2):
+            core.run(e_loc, d_loc, ix_local, kernel_events=evl[k])
+        tb.record()
+        torch.cuda.synchronize()
+        ms_l = ta.elapsed_time(tb) / 2
+        ms_lk = sum(a.elapsed_time(b) for a, b in evl) / 2
+        local = {"workload": f"neighbours = {m} of the {win} nearest cells on a ring embedding (cells in embedding order)",
+                 "value": C / (ms_l * 1e-3), "unit": UNIT, "ms_per_step": ms_l,
+                 "roofline_achieved_gbs": alg_bytes / (ms_lk * 1e-3) / 1e9, "frac": alg_bytes / (ms_lk * 1e-3) / 1e9 / peak}
+        del ix_local
+
     # ---------------- e2e: host buffers through the C ABI (N == 1) / the sharded host API (N > 1) -------
     e2e = None
     if not args.no_e2e:
@@ -280,6 +314,7 @@ def main():
                        "l2": "inputs (12 GB expression matrix, random row gather) exceed the 126 MB L2; no flush needed",
                        "step": "all-gather(e) [N>1] + cell_stats + k_coldeltacor + transition_prob"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "secondary_local_neighbours": local,
         }
         print(json.dumps(line))
     if world > 1:

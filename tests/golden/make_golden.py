@@ -171,6 +171,16 @@ def golden_smoothing(nb, out):
         res[f"w_dense_diag{diag}"] = np.asarray(sparse.csr_matrix(w).toarray())
         res[f"Sx_diag{diag}"] = np.asarray(nb.convolve_by_sparse_weights(S, w))
         res[f"Ux_diag{diag}"] = np.asarray(nb.convolve_by_sparse_weights(U, w))
+    # balanced kNN (neighbors.py:186-321): hub-limited graph, plain and group-constrained
+    rng2 = np.random.default_rng(7)
+    pts = np.concatenate([rng2.normal(size=(70, 4)), rng2.normal(size=(10, 4)) * 0.05])   # a tight hub cluster
+    groups = (np.arange(80) % 3).astype(np.int64)
+    for tag, cons in (("plain", None), ("grouped", groups)):
+        b = nb.BalancedKNN(k=8, sight_k=30, maxl=12, constraint=cons, mode="distance", n_jobs=1)
+        b.fit(pts)
+        gph = b.kneighbors_graph(mode="distance")
+        res[f"bknn_{tag}_data"], res[f"bknn_{tag}_indices"], res[f"bknn_{tag}_l"] = gph.data, gph.indices, b.l
+    res["bknn_points"], res["bknn_groups"] = pts, groups
     np.savez_compressed(os.path.join(out, "knn_smoothing_small.npz"), **res)
 
 
@@ -224,6 +234,14 @@ def golden_pipeline(an, out):
                delta_S_rndm=vlm.delta_S_rndm, corrcoef=vlm.corrcoef, corrcoef_random=vlm.corrcoef_random,
                transition_prob=vlm.transition_prob, transition_prob_random=vlm.transition_prob_random,
                delta_embedding=vlm.delta_embedding)
+    # expression scaling (analysis.py:1714-1731) on the same correlations
+    vlm.calculate_embedding_shift(sigma_corr=0.05, expression_scaling=True, scaling_penalty=1.0)
+    res.update(scaling=vlm.scaling, scaling_rndm=vlm.scaling_rndm, delta_embedding_scaled=vlm.delta_embedding,
+               delta_embedding_random_scaled=vlm.delta_embedding_random)
+    # transform="logratio" (analysis.py:1582-1590)
+    vlm.estimate_transition_prob(hidim="Sx_sz", embed="ts", transform="logratio", psc=1, n_neighbors=30,
+                                 knn_random=True, sampled_fraction=0.5, n_jobs=1, threads=1, calculate_randomized=False)
+    res.update(logratio_neigh_ixs=vlm.embedding_knn.indices.reshape(C, -1).copy(), logratio_corrcoef=vlm.corrcoef)
     # full (knn_random=False) mode on the same object
     vlm.estimate_transition_prob(hidim="Sx_sz", embed="ts", transform="sqrt", psc=1, n_neighbors=30,
                                  knn_random=False, calculate_randomized=False, n_jobs=1, threads=1)

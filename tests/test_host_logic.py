@@ -150,3 +150,16 @@ def test_velocytoloom_attribute_surface():
     assert vlm.Sx_sz.shape == (3, 4)
     with pytest.raises(AttributeError):
         vlm.Upred
+
+
+def test_balanced_knn_matches_reference_golden():
+    """Host-side restatement of BalancedKNN (neighbors.py:13-321) against the reference's own output."""
+    from velocyto_b200.neighbors import BalancedKNN
+    g = np.load(os.path.join(ROOT, "tests", "golden", "knn_smoothing_small.npz"))
+    pts, groups = g["bknn_points"], g["bknn_groups"]
+    for tag, cons in (("plain", None), ("grouped", groups)):
+        b = BalancedKNN(k=8, sight_k=30, maxl=12, constraint=cons, mode="distance", n_jobs=1).fit(pts)
+        gph = b.kneighbors_graph(mode="distance")
+        assert np.array_equal(gph.indices, g[f"bknn_{tag}_indices"])
+        np.testing.assert_allclose(gph.data, g[f"bknn_{tag}_data"], rtol=0, atol=0)
+        assert np.array_equal(b.l, g[f"bknn_{tag}_l"]) and b.l.max() <= 12

@@ -242,6 +242,17 @@ def test_velocytoloom_pipeline_matches_reference_golden(golden):
     np.testing.assert_allclose(vlm.transition_prob, g["transition_prob"], rtol=5e-5, atol=1e-12)
     np.testing.assert_allclose(vlm.transition_prob_random, g["transition_prob_random"], rtol=5e-5, atol=1e-12)
     np.testing.assert_allclose(vlm.delta_embedding, g["delta_embedding"], rtol=1e-4, atol=1e-7)
+    # expression scaling: two signed row-gathers + a cosine projection (analysis.py:1714-1731)
+    vlm.calculate_embedding_shift(sigma_corr=0.05, expression_scaling=True, scaling_penalty=1.0)
+    np.testing.assert_allclose(vlm.scaling, g["scaling"], rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(vlm.scaling_rndm, g["scaling_rndm"], rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(vlm.delta_embedding, g["delta_embedding_scaled"], rtol=3e-4, atol=1e-7)
+    np.testing.assert_allclose(vlm.delta_embedding_random, g["delta_embedding_random_scaled"], rtol=3e-4, atol=1e-7)
+    # transform="logratio" (analysis.py:1582-1590)
+    vlm.estimate_transition_prob(hidim="Sx_sz", embed="ts", transform="logratio", psc=1, n_neighbors=30, knn_random=True,
+                                 sampled_fraction=0.5, n_jobs=1, threads=1, calculate_randomized=False)
+    assert np.array_equal(vlm.neigh_ixs, g["logratio_neigh_ixs"])
+    np.testing.assert_allclose(vlm.corrcoef, g["logratio_corrcoef"], rtol=0, atol=3e-6)
     # full (all pairs) mode
     vlm.estimate_transition_prob(hidim="Sx_sz", embed="ts", transform="sqrt", psc=1, n_neighbors=30, knn_random=False,
                                  calculate_randomized=False, n_jobs=1, threads=1)

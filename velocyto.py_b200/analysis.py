@@ -125,14 +125,25 @@ class VelocytoLoom:
         N = self.S.shape[1]
         if k is None:
             k = int(N * 0.025)                                                          # analysis.py:983-984
-        if balanced:
-            raise NotImplementedError("balanced=True (BalancedKNN, neighbors.py:186-361: a sequential greedy pass) is "
-                                      "not part of the GPU hot path; build the graph with the reference and call "
-                                      "knn_imputation_precomputed")
-        if group_constraint is not None:
-            raise ValueError("group_constraint is currently supported only if the argument balanced is set to True")
+        if b_sight is None and balanced:
+            b_sight = np.maximum(int(k * 8), N - 1)                                     # analysis.py:985-988 (sic: maximum)
+        if b_maxl is None and balanced:
+            b_maxl = np.maximum(int(k * 4), N - 1)
         space = self.pcs[:, :n_pca_dims] if pca_space else self.S_norm.T                 # analysis.py:989-992
-        self.knn = knn_distance_matrix(space, metric=metric, k=k, mode="distance", n_jobs=n_jobs)
+        if balanced:                                                                     # analysis.py:993-1001
+            from .neighbors import BalancedKNN
+            constraint = None
+            if group_constraint is not None:
+                constraint = (np.array(self.cluster_ix) if isinstance(group_constraint, str) and group_constraint == "clusters"
+                              else np.asarray(group_constraint))
+            bknn = BalancedKNN(k=k, sight_k=b_sight, maxl=b_maxl, metric=metric, constraint=constraint, mode="distance",
+                               n_jobs=n_jobs)
+            bknn.fit(space)
+            self.knn = bknn.kneighbors_graph(mode="distance")
+        else:
+            if group_constraint is not None:
+                raise ValueError("group_constraint is currently supported only if the argument balanced is set to True")
+            self.knn = knn_distance_matrix(space, metric=metric, k=k, mode="distance", n_jobs=n_jobs)
         connectivity = (self.knn > 0).astype(float)                                      # analysis.py:1006
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -322,8 +333,6 @@ class VelocytoLoom:
             psc = 1. if transform in ("log", "logratio") else (1e-10 if transform == "sqrt" else 0)
         if transform not in ("log", "sqrt", "linear", "logratio"):
             raise NotImplementedError(f"transform={transform} is not a valid parameter")
-        if transform == "logratio":
-            raise NotImplementedError("transform='logratio' (log2 pre-transform of hidim, analysis.py:1582-1590) is not on the GPU path yet")
         if "pcs" in hidim:
             raise NotImplementedError("hidim='pcs' is not on the GPU path; use the expression space (default Sx_sz)")
         if ndims is not None:
@@ -335,10 +344,16 @@ class VelocytoLoom:
         C, G = e_cm.C, e_cm.G
         dS = self._dev("delta_S")
         used_dt = float(self.used_delta_t)
-        tname = {"log": "log10", "sqrt": "sqrt", "linear": "linear"}[transform]
+        tname = {"log": "log10", "sqrt": "sqrt", "linear": "linear", "logratio": "linear"}[transform]
+        hi_cm = e_cm
+        if transform == "logratio":
+            # correlate log2(hi_dim + psc) with log2(|hi_dim_t| + psc) - log2(hi_dim + psc), linear kernel (analysis.py:1582-1590)
+            e_cm = dev.logratio(hi_cm, None, 0.0, psc, 0)
 
         def transformed(delta_cm):
             # d = f(hi_dim_t - hi_dim), hi_dim_t = hi_dim + used_delta_t * delta_S   (analysis.py:1538, 1577/1594/1597)
+            if transform == "logratio":
+                return dev.logratio(hi_cm, delta_cm, used_dt, psc, 1)
             return dev.delta_transform(delta_cm, used_dt, tname, psc)
 
         d_cm = transformed(dS)
@@ -429,12 +444,15 @@ class VelocytoLoom:
                 setattr(self, pname, dev.scatter_dense(tp, ix_m, C).cpu().numpy())
         # delta_embedding = sum_j (P_ij - 1/k) * unit(emb_j - emb_i), neighbours only (analysis.py:1704-1712)
         for cname, pname in names:
-            de = dev.embedding_shift(getattr(self, "_" + pname + "_dev"), ix_m, self.embedding)
-            if expression_scaling:
-                raise NotImplementedError("expression_scaling=True needs two more (genes x cells) sparse products "
-                                          "(analysis.py:1714-1719): SURVEY.md 8f item 1, not built yet; pass "
-                                          "expression_scaling=False")
-            setattr(self, "delta_embedding" if pname == "transition_prob" else "delta_embedding_random", de.cpu().numpy())
+            tp = getattr(self, "_" + pname + "_dev")
+            de = dev.embedding_shift(tp, ix_m, self.embedding).cpu().numpy()
+            rnd = pname != "transition_prob"
+            if expression_scaling:                                                       # analysis.py:1714-1719, 1726-1731
+                sc = dev.expression_scaling(tp, ix_m, self._dev(self.which_hidim),
+                                            self._dev("delta_S_rndm" if rnd else "delta_S"), scaling_penalty).cpu().numpy()
+                setattr(self, "scaling_rndm" if rnd else "scaling", sc)
+                de = de * sc[:, None]
+            setattr(self, "delta_embedding_random" if rnd else "delta_embedding", de)
 
 
 for _n in _MATRIX_ATTRS:

@@ -174,7 +174,6 @@ __global__ void __launch_bounds__(256) k_delta_ops(const float *__restrict__ S, 
             } else if (mode == 4) r[k] = log2f(s[k] + psc);                                   // analysis.py:1582
             else r[k] = log2f(fabsf(s[k] + step) + psc) - log2f(s[k] + psc);                  // analysis.py:1583
         }
-        }
         reinterpret_cast<float4 *>(out)[t] = make_float4(r[0], r[1], r[2], r[3]);
     }
 }

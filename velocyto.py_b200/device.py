@@ -320,3 +320,25 @@ def fit_weights(kind: str, S: CellMajor, U: CellMajor, Sx: Optional[CellMajor] =
                0 if Ux is None else Ux.ptr, S.ld, S.G, S.C, float(maxmin_perc[0]), float(maxmin_perc[1]),
                W.ptr, W.ld, _stream_ptr())
     return W
+
+
+def logratio(S: CellMajor, delta_S: Optional[CellMajor], dt: float, psc: float, which: int) -> CellMajor:
+    """``transform="logratio"`` operands (analysis.py:1582-1583): 0 -> log2(S+psc), 1 -> log2(|S+dt*dS|+psc) - log2(S+psc)."""
+    out = CellMajor(torch.empty_like(S.t), S.G)
+    _cabi.call("velo_dev_logratio", S.ptr, 0 if delta_S is None else delta_S.ptr, out.ptr, S.ld, S.C, float(dt), float(psc),
+               int(which), _stream_ptr())
+    return out
+
+
+def expression_scaling(tp: torch.Tensor, ixs: torch.Tensor, hi_dim: CellMajor, delta_S: CellMajor,
+                       penalty: float = 1.0) -> torch.Tensor:
+    """``scaling`` of calculate_embedding_shift (analysis.py:1714-1719): the expected expression change
+    ``sum_n (P[c,n] - 1/m) * hi_dim[:, ixs[c,n]]`` (a K5 row gather with signed weights) projected on ``delta_S``."""
+    nc, m = tp.shape
+    indptr = torch.arange(0, nc * m + 1, m, device=tp.device, dtype=torch.int64)
+    w = (tp - 1.0 / m).reshape(-1).contiguous()
+    estim = knn_smooth(indptr, ixs.reshape(-1), w, hi_dim)
+    scale = torch.empty(nc, dtype=torch.float64, device=tp.device)
+    _cabi.call("velo_dev_row_cosine_scale", delta_S.ptr, estim.ptr, estim.ld, estim.G, nc, float(penalty), scale.data_ptr(),
+               _stream_ptr())
+    return scale
