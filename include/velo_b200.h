@@ -62,6 +62,8 @@ const char *velo_last_error(void);
 /* sm count, opt-in shared memory per block, total HBM bytes of the current device */
 int         velo_device_info(int *sm_count, int *smem_optin_bytes, size_t *hbm_bytes,
                              int *cc_major, int *cc_minor);
+/* give cached workspace (the stream-ordered pool this library allocates its scratch from) back to the driver */
+int         velo_release_workspace(void);
 /* number of kernel launches issued by this library in this process (bench evidence) */
 uint64_t    velo_launch_count(void);
 
@@ -187,6 +189,19 @@ int velo_dev_row_percentiles(const float *rows_gc, int64_t G, int64_t C, const d
 int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_cm, const float *Sx_cm,
                          const float *Ux_cm, int64_t ld, int64_t G, int64_t C, double perc_lo,
                          double perc_hi, float *W_cm, int64_t ldw, velo_stream_t stream);
+
+/* As velo_dev_fit_gammas with the non-default options: hi_per_gene (G fp64, device; limit_gamma's per-gene upper
+ * slope bound, estimation.py:199-204/229-234) and q_fixed (G fp64, device; fixperc_q's pinned offset,
+ * estimation.py:221-224/254-257); either may be NULL.  velo_dev_fit_constraints computes both from the data. */
+int velo_dev_fit_gammas_ex(int mode, const float *S_cm, const float *U_cm, int64_t ld,
+                           const float *W_cm, int64_t ldw, const uint8_t *cell_mask,
+                           int64_t G, int64_t C, double lo, double hi,
+                           const double *hi_per_gene, const double *q_fixed,
+                           float *gamma, float *offset, float *r2, double *moments, velo_stream_t stream);
+/* q_fix[g] = median(U[g, S[g,:] <= percentile(S[g,:], 1)]);  up_gamma[g] = median(U) > median(S) ?
+ * max(1.5, percentile(U[S > p90(S)], 10) / median(S[S > p90(S)])) : 1.5.  Outputs: G fp64 (device); either may be NULL. */
+int velo_dev_fit_constraints(const float *S_cm, const float *U_cm, int64_t ld, int64_t G, int64_t C,
+                             double *q_fix, double *up_gamma, velo_stream_t stream);
 
 /* ---- elementwise chain (K6): predict_U -> calculate_velocity -> calculate_shift ->
  * extrapolate_cell_at_t -> velocity transform (analysis.py:1343-1346,1369,1398-1406,1428-1431,1577/1597).

@@ -65,8 +65,8 @@ def test_argument_contract_is_checked_before_the_device():
         est.colDeltaCorpartial(e, e.astype(np.float32), ixs)
     with pytest.raises(ValueError):
         est.colDeltaCorLog10partial(e, e.copy(), ixs[:3])
-    with pytest.raises(NotImplementedError):
-        est.fit_slope_weighted(e, e, e, limit_gamma=True)
+    with pytest.raises(ValueError):
+        est.fit_slope(e, e[:, :3])
 
 
 def test_partition_covers_all_cells():

@@ -48,8 +48,17 @@ def test_fit_slopes_match_reference_golden(golden):
     close = np.abs(s[ok] - gs[ok]) <= 1e-3 * (1 + np.abs(gs[ok]))
     assert close.mean() >= 0.85
     assert np.array_equal(np.isnan(s), np.isnan(g["weighted_offset_g"]))
-    with pytest.raises(NotImplementedError):
-        est.fit_slope_offset(Y, X, fixperc_q=True)
+    # non-default options built on percentiles of masked subsets (device radix select):
+    # fixperc_q -> q = median(y[x <= p1(x)]) exactly, slope from SciPy's bounded Brent (xatol 1e-5)
+    s, q = est.fit_slope_offset(Y, X, fixperc_q=True)
+    np.testing.assert_allclose(q, g["slope_offset_fix_q"], rtol=1e-6, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(s, g["slope_offset_fix_g"], rtol=0, atol=3e-5, equal_nan=True)
+    s, q = est.fit_slope_weighted_offset(Y, X, W, fixperc_q=True, return_R2=False)
+    np.testing.assert_allclose(q, g["weighted_offset_fix_q"], rtol=1e-6, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(s, g["weighted_offset_fix_g"], rtol=0, atol=3e-5, equal_nan=True)
+    # limit_gamma -> per-gene upper bound max(1.5, p10(y[x > p90(x)]) / median(x[x > p90(x)]))
+    np.testing.assert_allclose(est.fit_slope_weighted(Y, X, W, limit_gamma=True), g["weighted_lim_g"], rtol=0, atol=3e-5,
+                               equal_nan=True)
 
 
 @pytest.mark.parametrize("mode", ["nnls", "ols", "weighted", "weighted_offset"])

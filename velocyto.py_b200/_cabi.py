@@ -29,6 +29,7 @@ PROTOTYPES = {
     "velo_last_error": (C.c_char_p, []),
     "velo_device_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(C.c_size_t), C.POINTER(_int), C.POINTER(_int)]),
     "velo_launch_count": (C.c_uint64, []),
+    "velo_release_workspace": (_int, []),
     # host drop-in tier
     "velo_colDeltaCor": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _int]),
     "velo_colDeltaCorSqrt": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _int, _dbl]),
@@ -52,6 +53,9 @@ PROTOTYPES = {
     "velo_dev_transition_prob": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _dbl, _ptr]),
     "velo_dev_fit_gammas": (_int, [_int, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _dbl, _dbl,
                                    _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "velo_dev_fit_gammas_ex": (_int, [_int, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _dbl, _dbl, _ptr, _ptr,
+                                      _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "velo_dev_fit_constraints": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "velo_dev_row_percentiles": (_int, [_ptr, _i64, _i64, _ptr, _int, _ptr, _ptr]),
     "velo_dev_fit_weights": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl, _ptr, _i64, _ptr]),
     "velo_dev_velocity_chain": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _int, _dbl, _dbl, _int, _int,

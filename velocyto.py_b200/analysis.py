@@ -188,9 +188,6 @@ class VelocytoLoom:
             nS, nU = ("Sx_sz", "Ux_sz") if use_size_norm else ("Sx", "Ux")               # analysis.py:1164-1177
         else:
             nS, nU = ("S_sz", "U_sz") if use_size_norm else ("S", "U")
-        if fixperc_q or limit_gamma:
-            raise NotImplementedError("fixperc_q / limit_gamma need per-gene percentiles of masked subsets "
-                                      "(estimation.py:199-204, 221-224): not on the GPU path yet")
         Sd, Ud = self._dev(nS), self._dev(nU)
         mask = None if self.steady_state.all() else self.steady_state
         Wd = None
@@ -198,16 +195,26 @@ class VelocytoLoom:
             Wd = self._fit_weights(weights, nS, nU, maxmin_perc, maxmin_weighted_pow)
         import torch
         mask_t = None if mask is None else torch.from_numpy(mask.astype(np.uint8))
-        if fit_offset:
+        # dispatch of analysis.py:1221-1257: fit_offset > fixperc_q > plain
+        use_fix = fixperc_q and not fit_offset
+        if fit_offset or use_fix:
             mode = dev.FIT_SLOPE_WEIGHTED_OFFSET if weighted else dev.FIT_SLOPE_OFFSET
         else:
             mode = dev.FIT_SLOPE_WEIGHTED if weighted else dev.FIT_SLOPE
-        lo = 1e-8 if mode == dev.FIT_SLOPE_WEIGHTED_OFFSET else 0.0
-        g, q, r2, _ = dev.fit_gammas(mode, Sd, Ud, Wd, mask_t, lo, 20.0, want_r2=weighted)
+        if limit_gamma and not weighted:
+            logging.warning("limit_gamma not implemented with this settings")            # analysis.py:1230,1242,1253
+        use_lim = limit_gamma and weighted and not use_fix
+        if mask is not None and (use_fix or use_lim):
+            raise NotImplementedError("fixperc_q / limit_gamma with a steady_state cell selection")
+        qf, up = dev.fit_constraints(Sd, Ud, use_fix, use_lim)
+        lo = 1e-8 if (mode == dev.FIT_SLOPE_WEIGHTED_OFFSET or use_lim) else 0.0
+        g, q, r2, _ = dev.fit_gammas(mode, Sd, Ud, Wd, mask_t, lo, 20.0, want_r2=weighted and not use_fix,
+                                     hi_per_gene=up, q_fixed=qf)
+        fit_offset = fit_offset or use_fix
         self._gamma_dev, self._q_dev = torch.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0), q
         self.gammas = g.cpu().numpy()
         self.q = q.cpu().numpy() if fit_offset else np.zeros_like(self.gammas)          # analysis.py:1250,1257
-        if weighted:
+        if r2 is not None:
             self.R2 = r2.cpu().numpy()
         self.gammas[~np.isfinite(self.gammas)] = 0                                      # analysis.py:1260
 

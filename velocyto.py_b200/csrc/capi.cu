@@ -58,6 +58,15 @@ int get_device_props(DeviceProps *out)
         set_error("device %d is sm_%d%d; libvelo_b200 is built for sm_100a only", dev, prop.major, prop.minor);
         return VELO_E_NODEVICE;
     }
+    // Workspace comes from the device's stream-ordered pool (cudaMallocAsync).  By default the pool hands memory
+    // back to the driver at every synchronisation, which turns each call's scratch (tens of MB for the fits, tens
+    // of GB for the host tier) into fresh driver allocations; keep it cached instead (velo_release_workspace trims).
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
     if (dev < 64) cache[dev] = dp;
     *out = dp;
     return VELO_OK;
@@ -199,6 +208,17 @@ static int host_coldeltacor(int transform, int rule, const void *e, const void *
 using namespace velo;
 
 extern "C" int velo_abi_version(void) { return VELO_ABI_VERSION; }
+
+extern "C" int velo_release_workspace(void)
+{
+    int dev = 0;
+    VELO_CUDA_TRY(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    VELO_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    VELO_CUDA_TRY(cudaDeviceSynchronize());
+    VELO_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    return VELO_OK;
+}
 extern "C" const char *velo_last_error(void) { return t_error.c_str(); }
 extern "C" uint64_t velo_launch_count(void) { return g_launches.load(); }
 

@@ -112,7 +112,8 @@ __device__ __forceinline__ double wls_obj(double m, double q, double sw, double 
 }
 
 __global__ void __launch_bounds__(128) k_fit_finalize(const double *__restrict__ partials, int parts, int64_t G,
-                                                      FitOpts opt, float *__restrict__ gamma,
+                                                      FitOpts opt, const double *__restrict__ hi_per_gene,
+                                                      const double *__restrict__ q_fixed, float *__restrict__ gamma,
                                                       float *__restrict__ offset, float *__restrict__ r2,
                                                       double *__restrict__ moments_out)
 {
@@ -131,12 +132,18 @@ __global__ void __launch_bounds__(128) k_fit_finalize(const double *__restrict__
     const double sw = mom[8], swx = mom[9], swy = mom[10], swxx = mom[11], swxy = mom[12], swyy = mom[13];
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     double m = 0.0, q = 0.0;
+    if (hi_per_gene) opt.hi = hi_per_gene[g];            // limit_gamma: per-gene upper slope bound (estimation.py:199-204)
     if (mom[6] == 0.0) {                 // not np.any(x): "definitely not at steady state" -> NaN
         m = nan;
         q = 0.0;
     } else if (mom[7] == 0.0) {          // not np.any(y)
         m = 0.0;
         q = 0.0;
+    } else if (q_fixed && (opt.mode == 1 || opt.mode == 3)) {
+        // fixperc_q: offset pinned to a low percentile of y, slope by bounded 1-D least squares on (0, 20)
+        // minimise sum w (x m - y + q)^2   (estimation.py:221-224, 254-257)
+        q = q_fixed[g];
+        m = opt.mode == 1 ? clampd((sxy - q * sx) / sxx, 0.0, 20.0) : clampd((swxy - q * swx) / swxx, 0.0, 20.0);
     } else if (opt.mode == 0) {
         m = sxy / sxx;
         if (m < 0.0) m = 0.0;            // nnls constraint
@@ -204,6 +211,15 @@ extern "C" int velo_dev_fit_gammas(int mode, const float *S_cm, const float *U_c
                                    int64_t ldw, const uint8_t *cell_mask, int64_t G, int64_t C, double lo, double hi,
                                    float *gamma, float *offset, float *r2, double *moments, velo_stream_t stream)
 {
+    return velo_dev_fit_gammas_ex(mode, S_cm, U_cm, ld, W_cm, ldw, cell_mask, G, C, lo, hi, nullptr, nullptr, gamma,
+                                  offset, r2, moments, stream);
+}
+
+extern "C" int velo_dev_fit_gammas_ex(int mode, const float *S_cm, const float *U_cm, int64_t ld, const float *W_cm,
+                                      int64_t ldw, const uint8_t *cell_mask, int64_t G, int64_t C, double lo, double hi,
+                                      const double *hi_per_gene, const double *q_fixed, float *gamma, float *offset,
+                                      float *r2, double *moments, velo_stream_t stream)
+{
     VELO_REQUIRE(mode >= 0 && mode <= 3, "fit_gammas: unknown mode %d", mode);
     VELO_REQUIRE(S_cm && U_cm && gamma && G > 0 && C > 0 && ld >= G, "fit_gammas: bad arguments");
     const bool weighted = mode >= 2;
@@ -239,7 +255,8 @@ extern "C" int velo_dev_fit_gammas(int mode, const float *S_cm, const float *U_c
     FitOpts opt{mode, lo, hi};
     if (e1 == cudaSuccess) {
         k_fit_finalize<<<static_cast<unsigned>(gblocks), threads, 0, st>>>(partials, static_cast<int>(parts), G, opt,
-                                                                           gamma, offset, r2, moments);
+                                                                           hi_per_gene, q_fixed, gamma, offset, r2,
+                                                                           moments);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e1 = cudaGetLastError();
     }

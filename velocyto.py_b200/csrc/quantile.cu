@@ -19,9 +19,27 @@ __device__ __forceinline__ float key2f(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// block-wide: the k-th smallest (0-based) element of row[0..n) and the (k+1)-th (== k-th if k == n-1)
-__device__ void block_select_pair(const float *__restrict__ row, int64_t n, int64_t k, float *v_lo, float *v_hi,
-                                  unsigned int *hist /*256*/, unsigned long long *scratch /*4*/)
+struct AllOf {
+    __device__ __forceinline__ bool operator()(int64_t) const { return true; }
+};
+// subset {i : key[i] <= thr} (le) or {i : key[i] > thr}
+struct KeyCmp {
+    const float *key;
+    double thr;
+    bool le;
+    __device__ __forceinline__ bool operator()(int64_t i) const
+    {
+        const double k = key[i];
+        return le ? (k <= thr) : (k > thr);
+    }
+};
+
+// block-wide: the k-th smallest (0-based) element of {row[i] : pred(i)} and the next one (== k-th if it is the last);
+// n_sub = size of the subset
+template <typename Pred>
+__device__ void block_select_pair(const float *__restrict__ row, int64_t n, int64_t n_sub, int64_t k, Pred pred,
+                                  float *v_lo, float *v_hi, unsigned int *hist /*256*/,
+                                  unsigned long long *scratch /*4*/)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     uint32_t prefix = 0, mask = 0;
@@ -32,6 +50,7 @@ __device__ void block_select_pair(const float *__restrict__ row, int64_t n, int6
         for (int b = tid; b < 256; b += nt) hist[b] = 0;
         __syncthreads();
         for (int64_t i = tid; i < n; i += nt) {
+            if (!pred(i)) continue;
             const uint32_t u = f2key(row[i]);
             if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         }
@@ -56,10 +75,11 @@ __device__ void block_select_pair(const float *__restrict__ row, int64_t n, int6
     }
     const float lo = key2f(prefix);
     float hi = lo;
-    if (k + 1 < n && rem + 1 >= static_cast<int64_t>(eq_count)) {
+    if (k + 1 < n_sub && rem + 1 >= static_cast<int64_t>(eq_count)) {
         // the next order statistic is the smallest key strictly above `prefix`
         uint32_t best = 0xffffffffu;
         for (int64_t i = tid; i < n; i += nt) {
+            if (!pred(i)) continue;
             const uint32_t u = f2key(row[i]);
             if (u > prefix && u < best) best = u;
         }
@@ -75,7 +95,42 @@ __device__ void block_select_pair(const float *__restrict__ row, int64_t n, int6
     *v_hi = hi;
 }
 
-// out[g*nq + j] = np.percentile(rows[g, :], q[j]) with the default "linear" method
+// np.percentile(subset of row, q) with the default "linear" method; every thread returns the value.
+// An empty subset gives NaN (as numpy does).
+template <typename Pred>
+__device__ double block_percentile(const float *__restrict__ row, int64_t n, double q, Pred pred, bool masked,
+                                   unsigned int *hist, unsigned long long *scratch)
+{
+    int64_t n_sub = n;
+    if (masked) {                                        // count the subset
+        unsigned int cnt = 0;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) cnt += pred(i) ? 1u : 0u;
+        if (threadIdx.x == 0) hist[0] = 0;
+        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&hist[0], cnt);
+        __syncthreads();
+        n_sub = hist[0];
+        __syncthreads();
+    }
+    if (n_sub == 0) return __longlong_as_double(0x7ff8000000000000LL);
+    const double pos = q / 100.0 * static_cast<double>(n_sub - 1);
+    int64_t k = static_cast<int64_t>(floor(pos));
+    if (k < 0) k = 0;
+    if (k > n_sub - 1) k = n_sub - 1;
+    const double t = pos - static_cast<double>(k);
+    float lo, hi;
+    block_select_pair(row, n, n_sub, k, pred, &lo, &hi, hist, scratch);
+    const double a = lo, b = hi;
+    // numpy's _lerp: a + (b-a)*t, evaluated from the right end for t >= 0.5
+    const double diff = b - a;
+    double r = a + diff * t;
+    if (t >= 0.5) r = b - diff * (1.0 - t);
+    if (t == 0.0) r = a;
+    return r;
+}
+
+// out[g*nq + j] = np.percentile(rows[g, :], q[j])
 __global__ void __launch_bounds__(256) k_row_percentiles(const float *__restrict__ rows, int64_t G, int64_t C,
                                                          const double *__restrict__ q, int nq, double *__restrict__ out)
 {
@@ -84,23 +139,49 @@ __global__ void __launch_bounds__(256) k_row_percentiles(const float *__restrict
     const int64_t g = blockIdx.x;
     const float *row = rows + g * C;
     for (int j = 0; j < nq; ++j) {
-        const double pos = q[j] / 100.0 * static_cast<double>(C - 1);
-        int64_t k = static_cast<int64_t>(floor(pos));
-        if (k < 0) k = 0;
-        if (k > C - 1) k = C - 1;
-        const double t = pos - static_cast<double>(k);
-        float lo, hi;
-        block_select_pair(row, C, k, &lo, &hi, hist, scratch);
-        if (threadIdx.x == 0) {
-            const double a = lo, b = hi;
-            // numpy's _lerp: a + (b-a)*t, evaluated from the right end for t >= 0.5
-            const double diff = b - a;
-            double r = a + diff * t;
-            if (t >= 0.5) r = b - diff * (1.0 - t);
-            if (t == 0.0) r = a;
-            out[g * nq + j] = r;
-        }
+        const double r = block_percentile(row, C, q[j], AllOf(), false, hist, scratch);
+        if (threadIdx.x == 0) out[g * nq + j] = r;
         __syncthreads();
+    }
+}
+
+// Per-gene constraints of the non-default fit options (x = spliced row, y = unspliced row, gene-major fp32):
+//   q_fix[g]    = median( y[x <= percentile(x, 1)] )                                 estimation.py:221, 254
+//   up_gamma[g] = median(y) > median(x) ? max(1.5, percentile(y[x > p90(x)], 10) / median(x[x > p90(x)])) : 1.5
+//                                                                                    estimation.py:199-204, 229-234
+__global__ void __launch_bounds__(256) k_fit_constraints(const float *__restrict__ xr, const float *__restrict__ yr,
+                                                         int64_t G, int64_t C, double *__restrict__ q_fix,
+                                                         double *__restrict__ up_gamma)
+{
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long scratch[4];
+    const int64_t g = blockIdx.x;
+    const float *x = xr + g * C, *y = yr + g * C;
+    if (q_fix) {
+        const double p1 = block_percentile(x, C, 1.0, AllOf(), false, hist, scratch);
+        __syncthreads();
+        const double v = block_percentile(y, C, 50.0, KeyCmp{x, p1, true}, true, hist, scratch);
+        if (threadIdx.x == 0) q_fix[g] = v;
+        __syncthreads();
+    }
+    if (up_gamma) {
+        const double my = block_percentile(y, C, 50.0, AllOf(), false, hist, scratch);
+        __syncthreads();
+        const double mx = block_percentile(x, C, 50.0, AllOf(), false, hist, scratch);
+        __syncthreads();
+        double up = 1.5;
+        if (my > mx) {                                       // uniform across the block
+            const double p90 = block_percentile(x, C, 90.0, AllOf(), false, hist, scratch);
+            __syncthreads();
+            const KeyCmp high{x, p90, false};
+            const double yy = block_percentile(y, C, 10.0, high, true, hist, scratch);
+            __syncthreads();
+            const double xx = block_percentile(x, C, 50.0, high, true, hist, scratch);
+            __syncthreads();
+            up = fmax(1.5, yy / xx);                         // np.maximum propagates NaN; fmax does not: patch below
+            if (yy != yy || xx != xx || (yy / xx) != (yy / xx)) up = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        if (threadIdx.x == 0) up_gamma[g] = up;
     }
 }
 
@@ -196,6 +277,9 @@ extern "C" int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_
     VELO_REQUIRE(S_cm && U_cm && W_cm && G > 0 && C > 0 && ld >= G && ldw >= G, "fit_weights: bad arguments");
     VELO_REQUIRE((kind != 0 && kind != 2) || (Sx_cm && Ux_cm), "fit_weights: maxmin_diag needs Sx and Ux");
     cudaStream_t st = as_stream(stream);
+    DeviceProps dp;
+    int rc0 = get_device_props(&dp);                       // also configures the workspace pool
+    if (rc0) return rc0;
     Tmp rows(st), X(st), perc(st), thr(st), qd(st), invS(st), invU(st);
     VELO_CUDA_TRY(rows.alloc(static_cast<size_t>(G) * C * 4));
     VELO_CUDA_TRY(X.alloc(static_cast<size_t>(C) * ld * 4));
@@ -242,6 +326,26 @@ extern "C" int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_
     if ((rc = denominators(S_cm, invS_p))) return rc;
     if ((rc = denominators(U_cm, invU_p))) return rc;
     k_scaled_combine<<<eg, 256, 0, st>>>(S_cm, U_cm, invS_p, invU_p, W_cm, ldw, G, C, kind == 3 ? 0 : 1);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+extern "C" int velo_dev_fit_constraints(const float *S_cm, const float *U_cm, int64_t ld, int64_t G, int64_t C,
+                                        double *q_fix, double *up_gamma, velo_stream_t stream)
+{
+    VELO_REQUIRE(S_cm && U_cm && G > 0 && C > 0 && ld >= G && (q_fix || up_gamma), "fit_constraints: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    DeviceProps dp;
+    int rc0 = get_device_props(&dp);
+    if (rc0) return rc0;
+    Tmp xr(st), yr(st);
+    VELO_CUDA_TRY(xr.alloc(static_cast<size_t>(G) * C * 4));
+    VELO_CUDA_TRY(yr.alloc(static_cast<size_t>(G) * C * 4));
+    int rc;
+    if ((rc = velo_dev_unpack_genemajor(S_cm, ld, G, C, xr.p, 4, stream))) return rc;
+    if ((rc = velo_dev_unpack_genemajor(U_cm, ld, G, C, yr.p, 4, stream))) return rc;
+    k_fit_constraints<<<static_cast<unsigned>(G), 256, 0, st>>>(static_cast<const float *>(xr.p),
+                                                               static_cast<const float *>(yr.p), G, C, q_fix, up_gamma);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }

@@ -199,9 +199,22 @@ def scatter_dense(compact: torch.Tensor, ixs: Optional[torch.Tensor], C: int, c0
 FIT_SLOPE, FIT_SLOPE_OFFSET, FIT_SLOPE_WEIGHTED, FIT_SLOPE_WEIGHTED_OFFSET = 0, 1, 2, 3
 
 
+def fit_constraints(S_cm: CellMajor, U_cm: CellMajor, fixperc_q: bool = False, limit_gamma: bool = False):
+    """Per-gene constraints of the non-default fit options: ``(q_fix, up_gamma)`` float64 CUDA vectors (or None).
+    Percentiles of masked subsets (estimation.py:199-204, 221-224) by radix select on the device."""
+    G, device = S_cm.G, S_cm.t.device
+    qf = torch.empty(G, dtype=torch.float64, device=device) if fixperc_q else None
+    up = torch.empty(G, dtype=torch.float64, device=device) if limit_gamma else None
+    if qf is not None or up is not None:
+        _cabi.call("velo_dev_fit_constraints", S_cm.ptr, U_cm.ptr, S_cm.ld, G, S_cm.C,
+                   0 if qf is None else qf.data_ptr(), 0 if up is None else up.data_ptr(), _stream_ptr())
+    return qf, up
+
+
 def fit_gammas(mode: int, S_cm: CellMajor, U_cm: CellMajor, W_cm: Optional[CellMajor] = None,
                cell_mask: Optional[torch.Tensor] = None, lo: float = 0.0, hi: float = 20.0,
-               want_r2: bool = False, want_moments: bool = False):
+               want_r2: bool = False, want_moments: bool = False,
+               hi_per_gene: Optional[torch.Tensor] = None, q_fixed: Optional[torch.Tensor] = None):
     """Batched per-gene fit (estimation.py:173-366).  Returns ``(gamma, offset, r2, moments)`` CUDA tensors
     (float32 ``(G,)``; ``r2`` / ``moments`` None unless requested)."""
     G, C, device = S_cm.G, S_cm.C, S_cm.t.device
@@ -215,9 +228,10 @@ def fit_gammas(mode: int, S_cm: CellMajor, U_cm: CellMajor, W_cm: Optional[CellM
         assert cell_mask.numel() == C
     if mode >= 2:
         assert W_cm is not None and W_cm.G == G and W_cm.C == C
-    _cabi.call("velo_dev_fit_gammas", mode, S_cm.ptr, U_cm.ptr, S_cm.ld,
+    _cabi.call("velo_dev_fit_gammas_ex", mode, S_cm.ptr, U_cm.ptr, S_cm.ld,
                0 if W_cm is None else W_cm.ptr, 0 if W_cm is None else W_cm.ld,
                0 if cell_mask is None else cell_mask.data_ptr(), G, C, float(lo), float(hi),
+               0 if hi_per_gene is None else hi_per_gene.data_ptr(), 0 if q_fixed is None else q_fixed.data_ptr(),
                gamma.data_ptr(), offset.data_ptr(), 0 if r2 is None else r2.data_ptr(),
                0 if mom is None else mom.data_ptr(), _stream_ptr())
     return gamma, offset, r2, mom

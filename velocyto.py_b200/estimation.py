@@ -108,7 +108,8 @@ def colDeltaCorSqrtpartial(emat: np.ndarray, dmat: np.ndarray, ixs: np.ndarray, 
 
 
 # --------------------------------------------------------------------------- gamma fits
-def _fit(mode: int, Y, X, W=None, lo: float = 0.0, hi: float = 20.0, want_r2: bool = False):
+def _fit(mode: int, Y, X, W=None, lo: float = 0.0, hi: float = 20.0, want_r2: bool = False,
+         fixperc_q: bool = False, limit_gamma: bool = False):
     """Upload (genes, cells) host matrices, run the batched fit kernel, return float32 host vectors."""
     from . import device as dev
     Y, X = np.asarray(Y), np.asarray(X)
@@ -121,7 +122,8 @@ def _fit(mode: int, Y, X, W=None, lo: float = 0.0, hi: float = 20.0, want_r2: bo
         if W.shape != Y.shape:
             raise ValueError("W must have the shape of Y")
         Wd = dev.CellMajor.from_gene_major(W.astype(np.float64, copy=False))
-    gamma, offset, r2, _ = dev.fit_gammas(mode, Xd, Yd, Wd, None, lo, hi, want_r2=want_r2)
+    qf, up = dev.fit_constraints(Xd, Yd, fixperc_q, limit_gamma)
+    gamma, offset, r2, _ = dev.fit_gammas(mode, Xd, Yd, Wd, None, lo, hi, want_r2=want_r2, hi_per_gene=up, q_fixed=qf)
     return (gamma.cpu().numpy(), offset.cpu().numpy(), None if r2 is None else r2.cpu().numpy())
 
 
@@ -133,10 +135,7 @@ def fit_slope(Y: np.ndarray, X: np.ndarray) -> np.ndarray:
 
 def fit_slope_offset(Y: np.ndarray, X: np.ndarray, fixperc_q: bool = False) -> Tuple[np.ndarray, np.ndarray]:
     """Per-gene OLS slope and intercept (velocyto/estimation.py:282-297; ``leastsq`` from (0, 0), :244-264)."""
-    if fixperc_q:
-        raise NotImplementedError("fixperc_q=True (percentile-pinned offset, estimation.py:254-257) is not on the "
-                                  "GPU path yet -- see DESIGN.md, out of scope this round")
-    g, q, _ = _fit(1, Y, X)
+    g, q, _ = _fit(1, Y, X, fixperc_q=fixperc_q)       # fixperc_q: q = median(y[x <= p1(x)]), slope bounded to (0, 20)
     return g, q
 
 
@@ -145,10 +144,7 @@ def fit_slope_weighted(Y: np.ndarray, X: np.ndarray, W: np.ndarray, return_R2: b
     """Per-gene weighted slope through the origin, bounded to (0, 20) (velocyto/estimation.py:300-334;
     ``minimize_scalar(bounded)``, :191-209).  As in the reference, ``bounds`` is accepted but the per-gene
     solver always runs with its default (0, 20) (estimation.py:319 does not forward it)."""
-    if limit_gamma:
-        raise NotImplementedError("limit_gamma=True (percentile-derived upper bound, estimation.py:199-204) is not "
-                                  "on the GPU path yet -- see DESIGN.md, out of scope this round")
-    g, _, r2 = _fit(2, Y, X, W, 0.0, 20.0, want_r2=return_R2)
+    g, _, r2 = _fit(2, Y, X, W, 1e-8 if limit_gamma else 0.0, 20.0, want_r2=return_R2, limit_gamma=limit_gamma)
     return (g, r2) if return_R2 else g
 
 
@@ -157,8 +153,7 @@ def fit_slope_weighted_offset(Y: np.ndarray, X: np.ndarray, W: np.ndarray, fixpe
     """Per-gene weighted slope + offset under box constraints ``m in [1e-8, 20]``, ``q in [0, 2 sum(yw)/sum(w)]``
     (velocyto/estimation.py:337-366; L-BFGS-B with numeric gradients, :212-241).  Returns the exact constrained
     optimum; SciPy's iterate differs from it by more than 1e-5 on a few percent of genes."""
-    if fixperc_q or limit_gamma:
-        raise NotImplementedError("fixperc_q / limit_gamma (percentile-derived constraints, estimation.py:221-234) are "
-                                  "not on the GPU path yet -- see DESIGN.md, out of scope this round")
-    g, q, r2 = _fit(3, Y, X, W, 1e-8, 20.0, want_r2=return_R2)
+    # fixperc_q takes precedence and ignores limit_gamma, as in the reference (estimation.py:220-224)
+    g, q, r2 = _fit(3, Y, X, W, 1e-8, 20.0, want_r2=return_R2, fixperc_q=fixperc_q,
+                    limit_gamma=limit_gamma and not fixperc_q)
     return (g, q, r2) if return_R2 else (g, q)
