@@ -247,6 +247,14 @@ int velo_dev_knn_smooth(const int64_t *indptr, const int32_t *indices, const flo
                         const float *S_cm, float *out_cm, int64_t ld, int64_t G, int64_t C,
                         int maximum, velo_stream_t stream);
 
+/* kNN smoothing of SPARSE counts (BASELINE config 5): S is CSR by cell (s_indptr C+1, s_genes sorted gene ids,
+ * s_values), the smoothing weights CSR by cell as above; writes the dense gene slab [g0, g0+ng) of the smoothed
+ * matrix: out_cm[c * ld_out + (g - g0)].  Deterministic (64-bit fixed-point shared-memory accumulation). */
+int velo_dev_knn_smooth_csr(const int64_t *w_indptr, const int32_t *w_indices, const float *w_weights,
+                            const int64_t *s_indptr, const int32_t *s_genes, const float *s_values,
+                            float *out_cm, int64_t ld_out, int64_t C, int64_t g0, int64_t ng, int maximum,
+                            velo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

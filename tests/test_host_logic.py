@@ -107,6 +107,40 @@ def _gloo_worker(rank, world, port, C, ld, q):
         dist.destroy_process_group()
 
 
+def _gloo_reshard_worker(rank, world, port, C, G, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from velocyto_b200.sharding import gene_partition, genes_to_cells, partition
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        full = torch.arange(C * G, dtype=torch.float32).reshape(C, G)
+        g0, ng = gene_partition(G, world)[rank]
+        c0, nc = partition(C, world)[rank]
+        got = genes_to_cells(full[:, g0:g0 + ng].clone(), G)
+        q.put((rank, bool(torch.equal(got, full[c0:c0 + nc]))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gene_to_cell_reshard_world2_gloo():
+    """Hand-over between the gene-sharded stages (K4/K5/K6) and the cell-sharded correlation: one all-to-all."""
+    import torch.multiprocessing as mp
+    from velocyto_b200.sharding import gene_partition
+    parts = gene_partition(100, 3)
+    assert sum(n for _, n in parts) == 100 and all(g0 % 32 == 0 for g0, n in parts if n)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_reshard_worker, args=(r, 2, port, 11, 70, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(q.get(timeout=5) for _ in range(2)) == {0: True, 1: True}
+
+
 @pytest.mark.parametrize("C", [10, 11])
 def test_all_gather_of_cell_blocks_world2_gloo(C):
     """The path's one exchange step: row index of the gathered buffer == global cell id (uneven C included)."""

@@ -165,8 +165,16 @@ class VelocytoLoom:
         import torch
         dv = dev.require_cuda()
         ip, ix, wt = (torch.from_numpy(indptr).to(dv), torch.from_numpy(indices).to(dv), torch.from_numpy(weights).to(dv))
-        Sx = dev.knn_smooth(ip, ix, wt, self._dev(src_s), maximum)
-        Ux = dev.knn_smooth(ip, ix, wt, self._dev(src_u), maximum)
+        host = self.__dict__.setdefault("_host", {})
+
+        def smooth(name):
+            # sparse counts (an extension: the reference is dense-only) stay CSR on the device and only the smoothed
+            # matrix is dense -- what makes the 500k-cell configuration fit (velo_dev_knn_smooth_csr)
+            if name in host and sparse.issparse(host[name]):
+                return dev.knn_smooth_csr(ip, ix, wt, sparse.csr_matrix(host[name].T), maximum=maximum)
+            return dev.knn_smooth(ip, ix, wt, self._dev(name), maximum)
+
+        Sx, Ux = smooth(src_s), smooth(src_u)
         self._set_dev("Sx", Sx)
         self._set_dev("Ux", Ux)
         # "a differently named variable for backwards compatibility" -- copies in the reference (analysis.py:1022-1023)

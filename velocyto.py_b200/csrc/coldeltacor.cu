@@ -188,7 +188,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                 const int nq = gl >> 2;                   // whole float4 groups
                 const float4 *s_e4 = reinterpret_cast<const float4 *>(s_e);
                 const float4 *s_b4 = reinterpret_cast<const float4 *>(s_b);
-                // Each warp streams whole neighbour rows.  The stream is software-pipelined in registers:
+                // Each warp streams whole neighbour rows.  The stream is software-pipelined in registers (cur / nxt).
+                // Measured alternative (profiles/r1_k1_ncu_v2.md): ping-pong buffers without the 16 register copies
+                // per group execute 19 % fewer instructions but run 10 % SLOWER -- with two load groups outstanding
+                // under different consumers the waits collapse onto the newest loads; the copies below double as the
+                // point where exactly one group is outstanding.
+                // The stream is software-pipelined in registers:
                 // while the 4 x 128-bit loads of group k are being consumed, those of group k+1 -- or of the
                 // first group of the warp's NEXT row -- are already in flight (8 loads = 128 B per lane,
                 // 64 KB per SM outstanding), which is what a random-row HBM gather needs to approach peak.
@@ -211,10 +216,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                 const float *lo_c_row = EXACT ? p.e_lo + cg * p.ld + g0 : nullptr;
                 int n = warp;
                 const float4 *row = nullptr;
-                float4 A[4], B[4];                           // ping-pong register buffers (no copies per group)
+                float4 cur[4];
                 if (n < mc) {
                     row = row_of(n);
-                    load_group(row, 0, A);
+                    load_group(row, 0, cur);
                 }
                 while (n < mc) {
                     const int n_next = n + kWarps;
@@ -222,43 +227,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                     Acc4 a;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) a.s1[k] = a.s2[k] = a.s3[k] = make_float2(0.0f, 0.0f);
-                    auto prefetch = [&](int base, float4(&v)[4]) {        // group `base` of this row, or the next row's first
-                        if (base + 128 <= nq) load_group_full(row, base, v);
-                        else if (base < nq) load_group(row, base, v);
-                        else if (row_next) load_group(row_next, 0, v);
-                    };
-                    auto consume = [&](int base, const float4(&v)[4]) {
+                    for (int base = 0; base < nq; base += 128) {          // warp-uniform trip count
+                        float4 nxt[4];
+                        if (base + 256 <= nq) load_group_full(row, base + 128, nxt);
+                        else if (base + 128 < nq) load_group(row, base + 128, nxt);
+                        else if (row_next) load_group(row_next, 0, nxt);
                         const int j = base + lane;
                         // residual rows (EXACT only): same offsets as the value rows, in the e_lo matrix
                         const float *lo_i = EXACT ? reinterpret_cast<const float *>(row + j) + lo_delta : nullptr;
                         const float *lo_c = EXACT ? lo_c_row + 4 * j : nullptr;
                         if (base + 128 <= nq) {                           // full group: no predicates
-                            accumulate4<TR, RULE, EXACT>(a, v[0], s_e4[j], s_b4[j], p.psc, lo_i, lo_c);
-                            accumulate4<TR, RULE, EXACT>(a, v[1], s_e4[j + 32], s_b4[j + 32], p.psc, lo_i + 128, lo_c + 128);
-                            accumulate4<TR, RULE, EXACT>(a, v[2], s_e4[j + 64], s_b4[j + 64], p.psc, lo_i + 256, lo_c + 256);
-                            accumulate4<TR, RULE, EXACT>(a, v[3], s_e4[j + 96], s_b4[j + 96], p.psc, lo_i + 384, lo_c + 384);
+                            accumulate4<TR, RULE, EXACT>(a, cur[0], s_e4[j], s_b4[j], p.psc, lo_i, lo_c);
+                            accumulate4<TR, RULE, EXACT>(a, cur[1], s_e4[j + 32], s_b4[j + 32], p.psc, lo_i + 128, lo_c + 128);
+                            accumulate4<TR, RULE, EXACT>(a, cur[2], s_e4[j + 64], s_b4[j + 64], p.psc, lo_i + 256, lo_c + 256);
+                            accumulate4<TR, RULE, EXACT>(a, cur[3], s_e4[j + 96], s_b4[j + 96], p.psc, lo_i + 384, lo_c + 384);
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 if (j + 32 * k < nq)
-                                    accumulate4<TR, RULE, EXACT>(a, v[k], s_e4[j + 32 * k], s_b4[j + 32 * k], p.psc,
+                                    accumulate4<TR, RULE, EXACT>(a, cur[k], s_e4[j + 32 * k], s_b4[j + 32 * k], p.psc,
                                                                  lo_i + 128 * k, lo_c + 128 * k);
                         }
-                    };
-                    bool next_in_B = false;                               // warp-uniform
-                    for (int base = 0; base < nq; base += 256) {          // two groups per trip: A then B
-                        prefetch(base + 128, B);
-                        consume(base, A);
-                        if (base + 128 < nq) {
-                            prefetch(base + 256, A);
-                            consume(base + 128, B);
-                        } else {
-                            next_in_B = true;                             // odd group count: next row's head sits in B
-                        }
-                    }
-                    if (next_in_B) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) A[k] = B[k];
+                        for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
                     }
                     const int64_t i = s_ix[n];
                     float s1 = (a.s1[0].x + a.s1[0].y) + (a.s1[1].x + a.s1[1].y);

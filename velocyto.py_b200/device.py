@@ -356,3 +356,30 @@ def expression_scaling(tp: torch.Tensor, ixs: torch.Tensor, hi_dim: CellMajor, d
     _cabi.call("velo_dev_row_cosine_scale", delta_S.ptr, estim.ptr, estim.ld, estim.G, nc, float(penalty), scale.data_ptr(),
                _stream_ptr())
     return scale
+
+
+def knn_smooth_csr(w_indptr, w_indices, w_weights, S_csr, g0: int = 0, ng: Optional[int] = None,
+                   maximum: bool = False) -> CellMajor:
+    """kNN smoothing with sparse counts.  ``S_csr``: scipy CSR ``(cells, genes)`` (or a ``(indptr, indices, data, G)``
+    tuple of arrays/tensors) with sorted column indices; returns the dense smoothed gene slab ``[g0, g0+ng)`` as a
+    ``(cells, ng)`` cell-major matrix (gene-sharding: every rank asks for its own slab)."""
+    device = require_cuda()
+    as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(
+        device=device, dtype=dt).contiguous()
+    if isinstance(S_csr, tuple):
+        s_ip, s_ix, s_v, G = S_csr
+    else:
+        S_csr = S_csr.tocsr()
+        if not S_csr.has_sorted_indices:
+            S_csr = S_csr.sorted_indices()
+        s_ip, s_ix, s_v, G = S_csr.indptr, S_csr.indices, S_csr.data, S_csr.shape[1]
+    s_ip, s_ix, s_v = as_t(s_ip, torch.int64), as_t(s_ix, torch.int32), as_t(s_v, torch.float32)
+    w_indptr, w_indices, w_weights = as_t(w_indptr, torch.int64), as_t(w_indices, torch.int32), as_t(w_weights, torch.float32)
+    C = w_indptr.numel() - 1
+    assert s_ip.numel() == C + 1
+    ng = G - g0 if ng is None else ng
+    out = CellMajor.empty(C, ng, device)
+    _cabi.call("velo_dev_knn_smooth_csr", w_indptr.data_ptr(), w_indices.data_ptr(), w_weights.data_ptr(),
+               s_ip.data_ptr(), s_ix.data_ptr(), s_v.data_ptr(), out.ptr, out.ld, C, int(g0), int(ng),
+               int(bool(maximum)), _stream_ptr())
+    return out

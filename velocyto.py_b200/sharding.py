@@ -85,3 +85,42 @@ class CellShardedTransitionProb:
         if self.sigma is None:
             return corr
         return dev.transition_prob(corr, ix_local, self.sigma, c0=self.c0, out=corr)
+
+
+# --------------------------------------------------------------------------- gene-sharded stages (K4 / K5 / K6)
+def gene_partition(G: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
+    """``(g0, ng)`` of every rank: contiguous gene blocks, starts aligned to ``align`` genes (128-byte rows)."""
+    b = (G + world - 1) // world
+    b = (b + align - 1) // align * align
+    return [(min(G, r * b), max(0, min(G, (r + 1) * b) - min(G, r * b))) for r in range(world)]
+
+
+def genes_to_cells(x_local: torch.Tensor, G: int, group=None) -> torch.Tensor:
+    """Re-shard from gene blocks to cell blocks: the hand-over between the gene-sharded stages
+    (kNN smoothing, gamma fit, elementwise chain -- every gene is independent) and the cell-sharded
+    correlation stage.
+
+    x_local: ``(C, ng_r)`` -- ALL cells, this rank's gene block (cell-major).  Returns ``(nc_r, G)``: this rank's
+    cell block (``partition``), all genes.  One all-to-all exchange; works on CUDA/NCCL and CPU/gloo tensors."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    C = x_local.shape[0]
+    if world == 1:
+        return x_local[:, :G].contiguous()
+    rank = dist.get_rank(group)
+    cparts, gparts = partition(C, world), gene_partition(G, world)
+    assert x_local.shape[1] >= gparts[rank][1]
+    ng = gparts[rank][1]
+    send = [x_local[c0:c0 + nc, :ng].contiguous() for c0, nc in cparts]        # my genes, each rank's cells
+    nc_me = cparts[rank][1]
+    recv = [torch.empty((nc_me, gparts[r][1]), dtype=x_local.dtype, device=x_local.device) for r in range(world)]
+    # pairwise exchange posted as one batch (NCCL fuses it into a single grouped all-to-all over NVLink; gloo,
+    # which has no alltoall, runs the same code in the CPU logic tests)
+    recv[rank].copy_(send[rank])
+    ops = []
+    for r in range(world):
+        if r != rank:
+            ops.append(dist.P2POp(dist.isend, send[r], r, group))
+            ops.append(dist.P2POp(dist.irecv, recv[r], r, group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return torch.cat(recv, dim=1)                                               # (nc_me, G) in gene order
