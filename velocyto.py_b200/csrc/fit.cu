@@ -235,9 +235,15 @@ extern "C" int velo_dev_fit_gammas_ex(int mode, const float *S_cm, const float *
     const int mthreads = 256;                                  // moments kernel: thread = 4 (2 if weighted) genes
     const int gp = weighted ? 2 : 4;
     const int64_t mblocks = ((G + gp - 1) / gp + mthreads - 1) / mthreads;
-    // enough cell-partitions to fill the machine a few times over, at least ~256 cells each
-    int64_t parts = (static_cast<int64_t>(dp.sm_count) * 4 + mblocks - 1) / mblocks;
-    if (parts > (C + 255) / 256) parts = (C + 255) / 256;
+    // cell partitions: fill the resident CTA slots of the machine exactly ONCE (a 2.03-wave grid runs as 3 waves)
+    int per_sm = 1;
+    if (weighted)
+        VELO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gene_moments<true, 2>, mthreads, 0));
+    else
+        VELO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gene_moments<false, 4>, mthreads, 0));
+    const int64_t slots = static_cast<int64_t>(dp.sm_count) * (per_sm > 0 ? per_sm : 1);
+    int64_t parts = slots / mblocks;                           // floor: never spill into a second wave
+    if (parts > (C + 63) / 64) parts = (C + 63) / 64;          // at least ~64 cells per partition
     if (parts < 1) parts = 1;
     if (parts > 65535) parts = 65535;
     const int64_t cpp = (C + parts - 1) / parts;
