@@ -370,3 +370,47 @@ def test_knn_smoothing_sparse_counts_matches_oracle(oracle):
     # same numbers as the dense-input kernel
     dense = dev.knn_smooth(wc.indptr, wc.indices, wc.data, dev.CellMajor.from_gene_major(S))
     np.testing.assert_allclose(full.to_gene_major(), dense.to_gene_major(), rtol=3e-7, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- BASELINE config-2 shape, size-independent properties
+def test_config2_shape_properties():
+    """10k cells x 20k genes, k = 500 (BASELINE config 2) -- too big for the oracle, so: linearity and constants of
+    the smoothing, exact recovery of a planted gamma, and agreement between the dense- and sparse-input kernels."""
+    import torch
+    from velocyto_b200 import device as dev
+    C, G, k = 10_000, 20_000, 500
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    X, Y = dev.CellMajor.empty(C, G), dev.CellMajor.empty(C, G)
+    X.t[:, :G] = torch.poisson(torch.rand((C, G), device="cuda", generator=gen) * 0.3)        # ~26 % non-zero
+    Y.t[:, :G] = torch.rand((C, G), device="cuda", generator=gen)
+    nbr = (torch.arange(C, device="cuda")[:, None] + torch.randint(1, C, (C, k), device="cuda", generator=gen)) % C
+    nbr = torch.cat([torch.arange(C, device="cuda")[:, None], nbr], 1).to(torch.int32).contiguous()
+    indptr = torch.arange(0, C * (k + 1) + 1, k + 1, device="cuda", dtype=torch.int64)
+    w = torch.full((C * (k + 1),), 1.0 / (k + 1), device="cuda", dtype=torch.float32)
+    sm = lambda M: dev.knn_smooth(indptr, nbr.view(-1), w, M)
+    Sx, Sy = sm(X), sm(Y)
+    # linearity: smooth(2X - 3Y) == 2 smooth(X) - 3 smooth(Y)
+    Z = dev.CellMajor((2 * X.t - 3 * Y.t).contiguous(), G)
+    lin = sm(Z).t[:, :G]
+    ref = 2 * Sx.t[:, :G] - 3 * Sy.t[:, :G]
+    assert float((lin - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    # a constant matrix is a fixed point (weights sum to one per cell)
+    K = dev.CellMajor(torch.full_like(X.t, 3.25), G)
+    assert float((sm(K).t[:, :G] - 3.25).abs().max()) < 1e-6
+    # sparse-input kernel == dense-input kernel on the same counts
+    Xs = X.t[:, :G].to_sparse_csr()
+    sp = dev.knn_smooth_csr(indptr, nbr.view(-1), w, (Xs.crow_indices(), Xs.col_indices(), Xs.values(), G))
+    assert float((sp.t[:, :G] - Sx.t[:, :G]).abs().max()) <= 3e-7 * float(Sx.t.abs().max()) + 1e-7
+    # planted slope: U = gamma * S + q exactly (up to fp32) -> OLS recovers gamma, q; nnls recovers gamma when q = 0
+    gam = torch.rand(G, device="cuda", generator=gen) + 0.05
+    q = torch.rand(G, device="cuda", generator=gen) * 0.1
+    U = dev.CellMajor((Sx.t * torch.nn.functional.pad(gam, (0, Sx.ld - G)) + torch.nn.functional.pad(q, (0, Sx.ld - G))).contiguous(), G)
+    g_hat, q_hat, _, _ = dev.fit_gammas(dev.FIT_SLOPE_OFFSET, Sx, U)
+    assert float(((g_hat - gam) / gam).abs().max()) < 2e-4 and float((q_hat - q).abs().max()) < 2e-5
+    U0 = dev.CellMajor((Sx.t * torch.nn.functional.pad(gam, (0, Sx.ld - G))).contiguous(), G)
+    g0, _, _, _ = dev.fit_gammas(dev.FIT_SLOPE, Sx, U0)
+    assert float(((g0 - gam) / gam).abs().max()) < 1e-6
+    # velocity of data that lies exactly on the fitted line is ~0 and extrapolation leaves S unchanged
+    out = dev.velocity_chain(Sx, U0, g0, None, want=("velocity", "S_t"))
+    assert float(out["velocity"].t.abs().max()) < 1e-5 * float(U0.t.abs().max()) + 1e-6
+    assert float((out["S_t"].t - Sx.t).abs().max()) < 1e-5
