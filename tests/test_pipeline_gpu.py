@@ -262,6 +262,16 @@ def test_velocytoloom_pipeline_matches_reference_golden(golden):
                                  sampled_fraction=0.5, n_jobs=1, threads=1, calculate_randomized=False)
     assert np.array_equal(vlm.neigh_ixs, g["logratio_neigh_ixs"])
     np.testing.assert_allclose(vlm.corrcoef, g["logratio_corrcoef"], rtol=0, atol=3e-6)
+    # hidim="pcs": correlation in principal-component space (analysis.py:1531-1533), checked against the oracle
+    from oracle import velo_oracle as vo
+    vlm.pcs_t = vlm.pcs + np.random.default_rng(3).normal(scale=0.3, size=vlm.pcs.shape)
+    vlm.estimate_transition_prob(hidim="pcs", embed="ts", transform="sqrt", psc=1, n_neighbors=30, knn_random=True,
+                                 sampled_fraction=0.5, n_jobs=1, threads=1, calculate_randomized=False)
+    hi, hi_t = np.ascontiguousarray(vlm.pcs.T), np.ascontiguousarray(vlm.pcs_t.T)
+    want = vo.patch_corrcoef(vo.colDeltaCorSqrtpartial(hi, vo.velocity_transform(hi_t - hi, "sqrt", 1.0), vlm.neigh_ixs, psc=1.0))
+    np.testing.assert_allclose(vlm.corrcoef, want, rtol=0, atol=2e-5)                 # 8 components only: no averaging of fp32 roundings
+    with pytest.raises(ValueError):
+        vlm.estimate_transition_prob(hidim="pcs", embed="ts", n_neighbors=30)          # randomised control needs delta_S
     # full (all pairs) mode
     vlm.estimate_transition_prob(hidim="Sx_sz", embed="ts", transform="sqrt", psc=1, n_neighbors=30, knn_random=False,
                                  calculate_randomized=False, n_jobs=1, threads=1)

@@ -348,17 +348,27 @@ class VelocytoLoom:
             psc = 1. if transform in ("log", "logratio") else (1e-10 if transform == "sqrt" else 0)
         if transform not in ("log", "sqrt", "linear", "logratio"):
             raise NotImplementedError(f"transform={transform} is not a valid parameter")
-        if "pcs" in hidim:
-            raise NotImplementedError("hidim='pcs' is not on the GPU path; use the expression space (default Sx_sz)")
-        if ndims is not None:
+        use_pcs = "pcs" in hidim                                                         # sic, analysis.py:1531
+        if use_pcs and calculate_randomized:
+            raise ValueError("calculate_randomized is not available with hidim='pcs' (the reference never builds the "
+                             "randomised displacement in that branch, analysis.py:1531-1533)")
+        if ndims is not None and not use_pcs:
             raise ValueError(f"ndims was set to {ndims} but hidim != 'pcs'. Set ndims = None for hidim='{hidim}'")
         if knn_random:
             np.random.seed(random_seed)                                                  # analysis.py:1529
         self.corr_calc = "knn_random" if knn_random else "full"
-        e_cm = self._dev(hidim, residual=True)
+        if use_pcs:
+            # principal-component space: rows = components, columns = cells (analysis.py:1532-1533)
+            hi = np.array(getattr(self, hidim).T[:, :ndims], order="C")
+            hi_t = np.array(getattr(self, hidim + "_t").T[:, :ndims], order="C")
+            e_cm = dev.CellMajor.from_gene_major(hi, residual=True)
+            dS = dev.CellMajor.from_gene_major(hi_t - hi)
+            used_dt = 1.0                                                                # delta = hi_dim_t - hi_dim directly
+        else:
+            e_cm = self._dev(hidim, residual=True)
+            dS = self._dev("delta_S")
+            used_dt = float(self.used_delta_t)
         C, G = e_cm.C, e_cm.G
-        dS = self._dev("delta_S")
-        used_dt = float(self.used_delta_t)
         tname = {"log": "log10", "sqrt": "sqrt", "linear": "linear", "logratio": "linear"}[transform]
         hi_cm = e_cm
         if transform == "logratio":
