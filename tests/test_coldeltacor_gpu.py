@@ -303,3 +303,21 @@ def test_full_size_properties_and_spot_check(oracle):
         d_sub[:, 1:] = 1.0 + np.arange(G)[:, None]     # any non-degenerate filler
         want = oracle.coldeltacor(e_sub, d_sub, sub_ix, "sqrt", 1.0)[0, 1:]
         np.testing.assert_allclose(out[c].cpu().numpy(), want, rtol=0, atol=5e-7)
+
+
+def test_empty_and_degenerate_shapes():
+    """No sampled neighbours, a single gene, a single cell: the wrappers return what the reference's loops leave behind
+    (untouched zeros; NaN for zero-variance pairs) instead of failing."""
+    import velocyto_b200.estimation as est
+    from velocyto_b200 import VeloError
+    e, d = synth(50, 12, 20)
+    out = est.colDeltaCorSqrtpartial(e, d, np.empty((12, 0), dtype=np.int64), psc=1.0)          # m == 0
+    assert out.shape == (12, 12) and not out.any()
+    comp = est.colDeltaCorSqrtpartial(e, d, np.empty((12, 0), dtype=np.int64), psc=1.0, compact=True)
+    assert comp.shape == (12, 0)
+    one_gene = est.colDeltaCorpartial(e[:1].copy(), d[:1].copy(), rand_ixs(12, 3, 21))               # G == 1: no variance
+    assert np.isnan(one_gene[np.arange(12)[:, None], rand_ixs(12, 3, 21)]).all()
+    one_cell = est.colDeltaCorSqrt(e[:, :1].copy(), d[:, :1].copy(), psc=1.0)                        # C == 1: only the self pair
+    assert one_cell.shape == (1, 1)
+    with pytest.raises(VeloError):
+        est.colDeltaCor(np.empty((0, 5)), np.empty((0, 5)))                                          # no genes at all
