@@ -255,6 +255,13 @@ int velo_dev_knn_smooth_csr(const int64_t *w_indptr, const int32_t *w_indices, c
                             float *out_cm, int64_t ld_out, int64_t C, int64_t g0, int64_t ng, int maximum,
                             velo_stream_t stream);
 
+/* Exact brute-force kNN (Euclidean) in a low-dimensional space: X is C x D fp64 row-major (device); writes the k
+ * nearest points of every point in ascending distance: out_idx (C x k int32), out_dist (C x k fp64 or NULL).
+ * include_self = 0 excludes the query point itself (scikit-learn's kneighbors with X=None, neighbors.py:370-376,
+ * analysis.py:1549); 1 keeps it (normally at rank 0; BalancedKNN's candidate lists, neighbors.py:282). k <= ~14000. */
+int velo_dev_knn(const double *X, int64_t C, int D, int k, int include_self,
+                 int32_t *out_idx, double *out_dist, velo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,16 @@ def main():
     dst = dev.CellMajor.empty(C, 4096)
     ms = timeit(lambda: _cabi.call("velo_dev_pack_cellmajor", src.data_ptr(), 8, 4096, C, dst.ptr, dst.ld, 0, torch.cuda.current_stream().cuda_stream))
     report("k_pack_cellmajor<double>", ms, 4096 * C * 12, shape=f"4096x{C}")
+    # exact kNN on the device (replaces scikit-learn's search)
+    pts = torch.randn((100_000, 2), device="cuda", dtype=torch.float64, generator=gen)
+    t0 = time.perf_counter(); dev.knn(pts, 3000); torch.cuda.synchronize(); t1 = time.perf_counter()
+    t0 = time.perf_counter(); dev.knn(pts, 3000); torch.cuda.synchronize(); t1 = time.perf_counter()
+    print(json.dumps(dict(kernel="k_knn_bruteforce 100000 points x 2-D, k=3000 (embedding neighbourhoods)", ms=(t1 - t0) * 1e3)))
+    pcs = torch.randn((C, 20), device="cuda", dtype=torch.float64, generator=gen)
+    dev.knn(pcs, k); torch.cuda.synchronize()
+    t0 = time.perf_counter(); dev.knn(pcs, k); torch.cuda.synchronize(); t1 = time.perf_counter()
+    print(json.dumps(dict(kernel=f"k_knn_bruteforce {C} points x 20-D, k={k} (knn_imputation search)", ms=(t1 - t0) * 1e3)))
+    del pts, pcs
     # full (all pairs) correlation, reduced config 3: G=30k, C=4k -> G*C^2 = 4.8e11 elements
     del S, U, Ux, W, src, dst
     Cf, Gf = 4000, 30_000

@@ -192,7 +192,7 @@ def test_balanced_knn_matches_reference_golden():
     g = np.load(os.path.join(ROOT, "tests", "golden", "knn_smoothing_small.npz"))
     pts, groups = g["bknn_points"], g["bknn_groups"]
     for tag, cons in (("plain", None), ("grouped", groups)):
-        b = BalancedKNN(k=8, sight_k=30, maxl=12, constraint=cons, mode="distance", n_jobs=1).fit(pts)
+        b = BalancedKNN(k=8, sight_k=30, maxl=12, constraint=cons, mode="distance", n_jobs=1, search="host").fit(pts)
         gph = b.kneighbors_graph(mode="distance")
         assert np.array_equal(gph.indices, g[f"bknn_{tag}_indices"])
         np.testing.assert_allclose(gph.data, g[f"bknn_{tag}_data"], rtol=0, atol=0)

@@ -424,3 +424,35 @@ def test_config2_shape_properties():
     out = dev.velocity_chain(Sx, U0, g0, None, want=("velocity", "S_t"))
     assert float(out["velocity"].t.abs().max()) < 1e-5 * float(U0.t.abs().max()) + 1e-6
     assert float((out["S_t"].t - Sx.t).abs().max()) < 1e-5
+
+
+# --------------------------------------------------------------------------- exact kNN on the device
+@pytest.mark.parametrize("D,k,include_self", [(2, 50, False), (2, 700, False), (20, 64, True), (7, 1, False)])
+def test_device_knn_matches_sklearn(D, k, include_self):
+    from sklearn.neighbors import NearestNeighbors
+    from velocyto_b200 import device as dev
+    rng = np.random.default_rng(91 + D + k)
+    X = rng.normal(size=(3000, D))
+    idx, dist = dev.knn(X, k, include_self)
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute").fit(X)
+    want_d, want_i = nn.kneighbors(X if include_self else None)
+    assert np.array_equal(idx.cpu().numpy(), want_i)
+    np.testing.assert_allclose(dist.cpu().numpy(), want_d, rtol=1e-12, atol=1e-12)
+
+
+def test_device_knn_graphs_match_reference_golden(golden):
+    """The kNN graphs the VelocytoLoom methods build on the device == the reference's scikit-learn graphs."""
+    from velocyto_b200.analysis import knn_distance_matrix, knn_graph_device
+    from velocyto_b200.neighbors import BalancedKNN
+    g = golden("pipeline_small.npz")
+    knn = knn_distance_matrix(g["pcs"][:, :6], metric="euclidean", k=9, mode="distance", n_jobs=1)
+    assert np.array_equal(knn.indices, g["knn_indices"]) and np.array_equal(knn.indptr, g["knn_indptr"])
+    np.testing.assert_allclose(knn.data, g["knn_data"], rtol=1e-12)
+    emb = knn_graph_device(g["embedding"], 31, "connectivity")
+    assert np.array_equal(emb.indices.reshape(-1, 31), g["full_knn_indices"])
+    s = golden("knn_smoothing_small.npz")
+    for tag, cons in (("plain", None), ("grouped", s["bknn_groups"])):
+        b = BalancedKNN(k=8, sight_k=30, maxl=12, constraint=cons, mode="distance", n_jobs=1).fit(s["bknn_points"])
+        gph = b.kneighbors_graph(mode="distance")
+        assert np.array_equal(gph.indices, s[f"bknn_{tag}_indices"])
+        np.testing.assert_allclose(gph.data, s[f"bknn_{tag}_data"], rtol=1e-12, atol=1e-15)

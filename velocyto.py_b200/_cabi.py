@@ -69,6 +69,7 @@ PROTOTYPES = {
     "velo_dev_embedding_shift": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _int, _i64, _i64, _i64, _ptr, _ptr]),
     "velo_dev_knn_smooth": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "velo_dev_knn_smooth_csr": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _ptr]),
+    "velo_dev_knn": (_int, [_ptr, _i64, _int, _int, _int, _ptr, _ptr, _ptr]),
 }
 
 _lib = None

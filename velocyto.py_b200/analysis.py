@@ -64,9 +64,23 @@ class _DeviceBacked:
         obj.__dict__.setdefault("_devs", {}).pop(self.name, None)
 
 
+def knn_graph_device(data: np.ndarray, k: int, mode: str = "connectivity", include_self: bool = False) -> sparse.csr_matrix:
+    """Euclidean kNN graph built by the brute-force device kernel (``velo_dev_knn``): the CSR scikit-learn's
+    ``kneighbors_graph(X=None, mode=...)`` returns -- k entries per row in ascending distance."""
+    from . import device as dev
+    idx, dist = dev.knn(np.ascontiguousarray(data, dtype=np.float64), k, include_self)
+    n = idx.shape[0]
+    vals = dist.cpu().numpy().ravel() if mode == "distance" else np.ones(n * k)
+    return sparse.csr_matrix((vals, idx.cpu().numpy().astype(np.int32).ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+
+
 def knn_distance_matrix(data: np.ndarray, metric: str = None, k: int = 40, mode: str = "connectivity",
                         n_jobs: int = 4) -> sparse.csr_matrix:
-    """k nearest neighbours NOT including the point itself (velocyto/neighbors.py:363-376); host, scikit-learn."""
+    """k nearest neighbours NOT including the point itself (velocyto/neighbors.py:363-376).  Euclidean searches run on
+    the device (exact, brute force); the correlation metric stays with scikit-learn on the host."""
+    from . import device as dev
+    if metric != "correlation" and k <= dev.KNN_MAX_K and np.shape(data)[1] <= 4096:
+        return knn_graph_device(data, k, mode)
     from sklearn.neighbors import NearestNeighbors
     if metric == "correlation":
         nn = NearestNeighbors(n_neighbors=k, metric="correlation", algorithm="brute", n_jobs=n_jobs)
@@ -390,9 +404,12 @@ class VelocytoLoom:
             d_rnd = transformed(self._dev("delta_S_rndm"))
         embedding = getattr(self, embed)
         self.embedding = embedding
-        nn = NearestNeighbors(n_neighbors=n_neighbors + 1, n_jobs=n_jobs)
-        nn.fit(embedding)
-        self.embedding_knn = nn.kneighbors_graph(mode="connectivity")                   # analysis.py:1547-1549
+        if n_neighbors + 1 <= dev.KNN_MAX_K:                                             # analysis.py:1547-1549, on the device
+            self.embedding_knn = knn_graph_device(np.asarray(embedding), n_neighbors + 1, "connectivity")
+        else:
+            nn = NearestNeighbors(n_neighbors=n_neighbors + 1, n_jobs=n_jobs)
+            nn.fit(embedding)
+            self.embedding_knn = nn.kneighbors_graph(mode="connectivity")
         if knn_random:
             neigh_ixs = self.embedding_knn.indices.reshape((-1, n_neighbors + 1))
             p = np.linspace(sampling_probs[0], sampling_probs[1], neigh_ixs.shape[1])

@@ -1,0 +1,180 @@
+// Exact brute-force k nearest neighbours in a low-dimensional space (PCA coordinates for knn_imputation,
+// analysis.py:989-1005 / neighbors.py:239-243,363-376; the 2-D embedding for estimate_transition_prob,
+// analysis.py:1547-1549).  Replaces scikit-learn's KD-tree search, which at 100k cells and k = 10^4 takes minutes
+// on the host.  SURVEY.md 8f item 2.
+//
+// One CTA per query cell (persistent grid).  The points (C x D fp64) stay L2 resident; per query:
+//   1. squared Euclidean distances in fp64, their order-preserving fp32 keys to a per-CTA scratch row;
+//   2. 8-bit-per-pass radix select of the k-th smallest key (shared-memory histograms);
+//   3. compaction of the candidates (key <= threshold; a handful more than k when fp32 keys tie), with their exact
+//      fp64 distances, into shared memory;
+//   4. bitonic sort by (distance, index) and write-out of the k nearest in ascending order.
+// Distances are evaluated directly as sum (x_q - x_j)^2 (no |x|^2+|y|^2-2xy cancellation), in fp64 like the reference.
+#include "velo_common.cuh"
+
+namespace velo {
+
+__device__ __forceinline__ uint32_t knn_f2key(float f)   // f >= 0
+{
+    return __float_as_uint(f);                            // non-negative floats order like their bit patterns
+}
+
+struct KnnParams {
+    const double *X;       // C x D
+    int64_t C;
+    int D, k, include_self, P;
+    int32_t *out_idx;      // C x k
+    double *out_dist;      // C x k or null
+    uint32_t *scratch;     // gridDim.x x C
+    int *overflow;         // set to 1 when more than P candidates tie at the threshold
+};
+
+__global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    double *c_key = reinterpret_cast<double *>(sm_raw);                  // P
+    int32_t *c_idx = reinterpret_cast<int32_t *>(c_key + p.P);           // P
+    double *xq = reinterpret_cast<double *>(c_idx + p.P);                // D (P even -> 8-byte aligned)
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long sel[3];
+    __shared__ unsigned int n_cand;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    uint32_t *keys = p.scratch + static_cast<int64_t>(blockIdx.x) * p.C;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (int64_t q = blockIdx.x; q < p.C; q += gridDim.x) {
+        for (int d = tid; d < p.D; d += nt) xq[d] = p.X[q * p.D + d];
+        __syncthreads();
+        // 1. distances -> keys
+        for (int64_t j = tid; j < p.C; j += nt) {
+            double d2 = 0.0;
+            const double *xj = p.X + j * p.D;
+            for (int d = 0; d < p.D; ++d) {
+                const double t = xj[d] - xq[d];
+                d2 = fma(t, t, d2);
+            }
+            const bool skip = !p.include_self && j == q;
+            keys[j] = skip ? 0x7f800000u : knn_f2key(static_cast<float>(d2));   // +inf key for the query itself
+        }
+        __syncthreads();
+        // 2. radix select of the k-th smallest key (0-based rank k-1)
+        uint32_t prefix = 0, mask = 0;
+        int64_t rem = p.k - 1;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int b = tid; b < 256; b += nt) hist[b] = 0;
+            __syncthreads();
+            for (int64_t j = tid; j < p.C; j += nt) {
+                const uint32_t u = keys[j];
+                if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int64_t cum = 0;
+                int b = 0;
+                for (; b < 255; ++b) {
+                    if (cum + hist[b] > rem) break;
+                    cum += hist[b];
+                }
+                sel[0] = static_cast<unsigned long long>(b);
+                sel[1] = static_cast<unsigned long long>(rem - cum);
+            }
+            __syncthreads();
+            prefix |= static_cast<uint32_t>(sel[0]) << shift;
+            mask |= 255u << shift;
+            rem = static_cast<int64_t>(sel[1]);
+            __syncthreads();
+        }
+        // 3. candidates: every key <= threshold, with exact fp64 distances
+        if (tid == 0) n_cand = 0;
+        for (int i = tid; i < p.P; i += nt) {
+            c_key[i] = inf;
+            c_idx[i] = 0x7fffffff;
+        }
+        __syncthreads();
+        for (int64_t j = tid; j < p.C; j += nt) {
+            if (keys[j] <= prefix && (p.include_self || j != q)) {
+                const unsigned int slot = atomicAdd(&n_cand, 1u);
+                if (slot < static_cast<unsigned int>(p.P)) {
+                    double d2 = 0.0;
+                    const double *xj = p.X + j * p.D;
+                    for (int d = 0; d < p.D; ++d) {
+                        const double t = xj[d] - xq[d];
+                        d2 = fma(t, t, d2);
+                    }
+                    c_key[slot] = d2;
+                    c_idx[slot] = static_cast<int32_t>(j);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && n_cand > static_cast<unsigned int>(p.P)) atomicExch(p.overflow, 1);
+        // 4. bitonic sort by (distance, index)
+        for (int kk = 2; kk <= p.P; kk <<= 1)
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                for (int t = tid; t < p.P; t += nt) {
+                    const int l = t ^ jj;
+                    if (l > t) {
+                        const double a = c_key[t], b = c_key[l];
+                        const int32_t ia = c_idx[t], ib = c_idx[l];
+                        const bool gt = a > b || (a == b && ia > ib);
+                        if (gt == ((t & kk) == 0)) {
+                            c_key[t] = b; c_key[l] = a;
+                            c_idx[t] = ib; c_idx[l] = ia;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int r = tid; r < p.k; r += nt) {
+            p.out_idx[q * p.k + r] = c_idx[r];
+            if (p.out_dist) p.out_dist[q * p.k + r] = sqrt(c_key[r]);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace velo
+
+using namespace velo;
+
+extern "C" int velo_dev_knn(const double *X, int64_t C, int D, int k, int include_self, int32_t *out_idx,
+                            double *out_dist, velo_stream_t stream)
+{
+    VELO_REQUIRE(X && out_idx && C > 0 && D > 0 && D <= 4096, "knn: bad arguments");
+    VELO_REQUIRE(k > 0 && k <= (include_self ? C : C - 1), "knn: k = %d out of range for %lld points", k,
+                 static_cast<long long>(C));
+    VELO_REQUIRE(C < 2147483647LL, "knn: too many points");
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    int P = 64;
+    while (P < k + (k >> 3) + 32) P <<= 1;                 // room for fp32-key ties at the threshold
+    const size_t smem = static_cast<size_t>(P) * 12 + static_cast<size_t>(D) * 8 + 16;
+    VELO_REQUIRE(smem + 2048 <= static_cast<size_t>(dp.smem_optin), "knn: k = %d too large for shared memory (max ~14000)", k);
+    cudaStream_t st = as_stream(stream);
+    VELO_CUDA_TRY(cudaFuncSetAttribute(k_knn_bruteforce, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 1;
+    VELO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_knn_bruteforce, 512, smem));
+    int64_t grid = static_cast<int64_t>(dp.sm_count) * (per_sm > 0 ? per_sm : 1);
+    if (grid > C) grid = C;
+    uint32_t *scratch = nullptr;
+    int *overflow = nullptr;
+    VELO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), static_cast<size_t>(grid) * C * 4, st));
+    VELO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&overflow), sizeof(int), st));
+    VELO_CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+    KnnParams p;
+    p.X = X; p.C = C; p.D = D; p.k = k; p.include_self = include_self; p.P = P;
+    p.out_idx = out_idx; p.out_dist = out_dist; p.scratch = scratch; p.overflow = overflow;
+    k_knn_bruteforce<<<static_cast<unsigned>(grid), 512, smem, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    int flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, overflow, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(scratch, st);
+    cudaFreeAsync(overflow, st);
+    VELO_CUDA_TRY(e);
+    VELO_REQUIRE(flag == 0, "knn: more than %d points tie with the k-th neighbour distance (duplicated points?)", P - k);
+    return VELO_OK;
+}

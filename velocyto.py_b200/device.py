@@ -383,3 +383,21 @@ def knn_smooth_csr(w_indptr, w_indices, w_weights, S_csr, g0: int = 0, ng: Optio
                s_ip.data_ptr(), s_ix.data_ptr(), s_v.data_ptr(), out.ptr, out.ld, C, int(g0), int(ng),
                int(bool(maximum)), _stream_ptr())
     return out
+
+
+# --------------------------------------------------------------------------- exact kNN
+KNN_MAX_K = 14000
+
+
+def knn(points, k: int, include_self: bool = False):
+    """Exact Euclidean k nearest neighbours of every row of ``points`` (C x D), ascending by distance.
+    Returns ``(idx int32 (C, k), dist float64 (C, k))`` CUDA tensors."""
+    device = require_cuda()
+    X = (points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)))
+    X = X.to(device=device, dtype=torch.float64).contiguous()
+    C, D = X.shape
+    idx = torch.empty((C, k), dtype=torch.int32, device=device)
+    dist = torch.empty((C, k), dtype=torch.float64, device=device)
+    _cabi.call("velo_dev_knn", X.data_ptr(), C, D, int(k), int(bool(include_self)), idx.data_ptr(), dist.data_ptr(),
+               _stream_ptr())
+    return idx, dist

@@ -114,8 +114,11 @@ class BalancedKNN:
     (velocyto/neighbors.py:186-321): ``fit`` -> ``kneighbors`` / ``kneighbors_graph``."""
 
     def __init__(self, k: int = 50, sight_k: int = 100, maxl: int = 200, constraint: np.ndarray = None,
-                 mode: str = "distance", metric: str = "euclidean", n_jobs: int = 4) -> None:
+                 mode: str = "distance", metric: str = "euclidean", n_jobs: int = 4, search: str = "device") -> None:
+        # search="device": candidate lists from the brute-force GPU kernel (Euclidean); "host": scikit-learn, as the
+        # reference does (explicit opt-in, also what the correlation metric uses)
         self.k, self.sight_k, self.maxl, self.mode, self.metric, self.n_jobs = k, sight_k, maxl, mode, metric, n_jobs
+        self.search = search
         self.constraint = constraint
         self.dist_new = self.dsi_new = self.l = None
         self.bknn = None
@@ -141,7 +144,14 @@ class BalancedKNN:
             self.data = X
         if maxl is not None:
             self.maxl = maxl
-        self.dist, self.dsi = self.nn.kneighbors(self.data, return_distance=True)
+        from . import device as dev
+        if (self.search == "device" and self.metric != "correlation" and self.sight_k + 1 <= dev.KNN_MAX_K
+                and self.data is self.fitdata):
+            # candidate lists (self included, ascending distance) from the brute-force device kernel
+            idx, dist = dev.knn(np.ascontiguousarray(self.fitdata, dtype=np.float64), self.sight_k + 1, include_self=True)
+            self.dist, self.dsi = dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+        else:
+            self.dist, self.dsi = self.nn.kneighbors(self.data, return_distance=True)
         self.dist_new, self.dsi_new, self.l = knn_balance(self.dsi, self.dist, maxl=self.maxl, k=self.k,
                                                           constraint=self.constraint)
         return self.dist_new, self.dsi_new, self.l
