@@ -434,7 +434,8 @@ def test_device_knn_matches_sklearn(D, k, include_self):
     rng = np.random.default_rng(91 + D + k)
     X = rng.normal(size=(3000, D))
     idx, dist = dev.knn(X, k, include_self)
-    nn = NearestNeighbors(n_neighbors=k, algorithm="brute").fit(X)
+    # kd_tree: exact sum-of-squares distances (scikit-learn's brute force expands |x|^2+|y|^2-2xy and is 1e-8 noisy)
+    nn = NearestNeighbors(n_neighbors=k, algorithm="kd_tree").fit(X)
     want_d, want_i = nn.kneighbors(X if include_self else None)
     assert np.array_equal(idx.cpu().numpy(), want_i)
     np.testing.assert_allclose(dist.cpu().numpy(), want_d, rtol=1e-12, atol=1e-12)
@@ -445,11 +446,16 @@ def test_device_knn_graphs_match_reference_golden(golden):
     from velocyto_b200.analysis import knn_distance_matrix, knn_graph_device
     from velocyto_b200.neighbors import BalancedKNN
     g = golden("pipeline_small.npz")
+    C = g["pcs"].shape[0]
     knn = knn_distance_matrix(g["pcs"][:, :6], metric="euclidean", k=9, mode="distance", n_jobs=1)
+    assert (np.diff(knn.data.reshape(C, 9), axis=1) >= 0).all()          # rows in ascending distance, like kneighbors()
+    knn.sort_indices()                                                    # the golden graph was canonicalised by `knn > 0`
     assert np.array_equal(knn.indices, g["knn_indices"]) and np.array_equal(knn.indptr, g["knn_indptr"])
     np.testing.assert_allclose(knn.data, g["knn_data"], rtol=1e-12)
-    emb = knn_graph_device(g["embedding"], 31, "connectivity")
-    assert np.array_equal(emb.indices.reshape(-1, 31), g["full_knn_indices"])
+    emb = knn_graph_device(g["embedding"], 31, "connectivity").indices.reshape(C, 31)
+    # the sampler indexes neighbours by RANK: rank order must match scikit-learn's (analysis.py:1552-1566)
+    assert np.array_equal(emb[np.arange(C)[:, None], g["sampling_ixs"]], g["neigh_ixs"])
+    assert np.array_equal(np.sort(emb, 1), np.sort(g["full_knn_indices"], 1))
     s = golden("knn_smoothing_small.npz")
     for tag, cons in (("plain", None), ("grouped", s["bknn_groups"])):
         b = BalancedKNN(k=8, sight_k=30, maxl=12, constraint=cons, mode="distance", n_jobs=1).fit(s["bknn_points"])
