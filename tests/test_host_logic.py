@@ -197,3 +197,23 @@ def test_balanced_knn_matches_reference_golden():
         assert np.array_equal(gph.indices, g[f"bknn_{tag}_indices"])
         np.testing.assert_allclose(gph.data, g[f"bknn_{tag}_data"], rtol=0, atol=0)
         assert np.array_equal(b.l, g[f"bknn_{tag}_l"]) and b.l.max() <= 12
+
+
+def test_connectivity_with_diagonal_equals_scipy_path():
+    """Fast CSR construction == ``(knn > 0).astype(float); setdiag(diag)`` of the reference (analysis.py:1006-1009)."""
+    import warnings
+    from scipy import sparse
+    from velocyto_b200.analysis import connectivity_with_diagonal
+    rng = np.random.default_rng(5)
+    n, k = 60, 7
+    idx = np.stack([rng.choice(n, k, replace=False) for _ in range(n)])            # may contain the diagonal
+    dist = rng.uniform(0.1, 1.0, (n, k))
+    dist[rng.uniform(size=dist.shape) < 0.1] = 0.0                                  # zero-distance edges are dropped
+    knn = sparse.csr_matrix((dist.ravel(), idx.ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+    for diag in (1, 8, 0.5):
+        want = (knn > 0).astype(float)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want.setdiag(diag)
+        got = connectivity_with_diagonal(knn, diag)
+        assert np.array_equal(got.toarray(), want.toarray())

@@ -73,17 +73,29 @@ struct Acc4 {                // 4-way interleaved partial sums, kept as two fp32
 // and for psc > 0 the transforms jump by 2*f(0+) across zero.  Rounding is monotone, so the fp32 difference has
 // the right sign whenever it is non-zero; only exact fp32 ties of non-zero values need the residuals, and those
 // are rare (one global load pair per tie).  lo_i / lo_c point at the residuals of the same four genes.
-template <int TR, int RULE, bool EXACT>
-__device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float4 ec, const float4 b, float psc,
-                                            const float *lo_i, const float *lo_c)
+struct Diff4 {                 // the four differences of one float4 of genes, plus the EXACT tie flag
+    float2 t01, t23;
+    bool tie;
+};
+
+template <bool EXACT>
+__device__ __forceinline__ Diff4 diff4(const float4 v, const float4 ec)
 {
-    const float2 t01 = sub2(make_float2(v.x, v.y), make_float2(ec.x, ec.y));
-    const float2 t23 = sub2(make_float2(v.z, v.w), make_float2(ec.z, ec.w));
-    float t0 = t01.x, t1 = t01.y, t2 = t23.x, t3 = t23.y;
+    Diff4 d;
+    d.t01 = sub2(make_float2(v.x, v.y), make_float2(ec.x, ec.y));
+    d.t23 = sub2(make_float2(v.z, v.w), make_float2(ec.z, ec.w));
+    d.tie = EXACT && (((v.x == ec.x) & (v.x != 0.0f)) | ((v.y == ec.y) & (v.y != 0.0f)) |
+                      ((v.z == ec.z) & (v.z != 0.0f)) | ((v.w == ec.w) & (v.w != 0.0f)));
+    return d;
+}
+
+template <int TR, int RULE, bool EXACT>
+__device__ __forceinline__ void accumulate_diff(Acc4 &a, const Diff4 d, const float4 b, float psc, const float *lo_i,
+                                                const float *lo_c)
+{
+    float t0 = d.t01.x, t1 = d.t01.y, t2 = d.t23.x, t3 = d.t23.y;
     if (EXACT) {
-        const bool tie = ((v.x == ec.x) & (v.x != 0.0f)) | ((v.y == ec.y) & (v.y != 0.0f)) |
-                         ((v.z == ec.z) & (v.z != 0.0f)) | ((v.w == ec.w) & (v.w != 0.0f));
-        if (tie) {
+        if (d.tie) {
             const float4 li = __ldg(reinterpret_cast<const float4 *>(lo_i));
             const float4 lc = __ldg(reinterpret_cast<const float4 *>(lo_c));
             if (t0 == 0.0f) t0 = li.x - lc.x;
@@ -99,6 +111,12 @@ __device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float
     a.s1[1] = add2(a.s1[1], A23); a.s2[1] = fma2(A23, A23, a.s2[1]); a.s3[1] = fma2(A23, make_float2(b.z, b.w), a.s3[1]);
 }
 
+template <int TR, int RULE, bool EXACT>
+__device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float4 ec, const float4 b, float psc,
+                                            const float *lo_i, const float *lo_c)
+{
+    accumulate_diff<TR, RULE, EXACT>(a, diff4<EXACT>(v, ec), b, psc, lo_i, lo_c);
+}
 template <int TR, int RULE, bool EXACT>
 __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
 {
@@ -188,11 +206,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                 const int nq = gl >> 2;                   // whole float4 groups
                 const float4 *s_e4 = reinterpret_cast<const float4 *>(s_e);
                 const float4 *s_b4 = reinterpret_cast<const float4 *>(s_b);
-                // Each warp streams whole neighbour rows.  The stream is software-pipelined in registers (cur / nxt).
-                // Measured alternative (profiles/r1_k1_ncu_v2.md): ping-pong buffers without the 16 register copies
-                // per group execute 19 % fewer instructions but run 10 % SLOWER -- with two load groups outstanding
-                // under different consumers the waits collapse onto the newest loads; the copies below double as the
-                // point where exactly one group is outstanding.
+                // Each warp streams whole neighbour rows, software-pipelined in ONE register buffer: the differences
+                // e_i - e_c are formed first (the only consumers of the loaded values), then the next group's loads
+                // are issued into the same registers and fly during the transform/accumulate math.
+                // Measured alternatives (profiles/): a second buffer with 16 register copies per group (+2
+                // instructions per element), and ping-pong buffers without copies, 10 % SLOWER -- two groups
+                // outstanding under different consumers make the waits collapse onto the newest loads.
                 // The stream is software-pipelined in registers:
                 // while the 4 x 128-bit loads of group k are being consumed, those of group k+1 -- or of the
                 // first group of the warp's NEXT row -- are already in flight (8 loads = 128 B per lane,
@@ -228,28 +247,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
 #pragma unroll
                     for (int k = 0; k < 2; ++k) a.s1[k] = a.s2[k] = a.s3[k] = make_float2(0.0f, 0.0f);
                     for (int base = 0; base < nq; base += 128) {          // warp-uniform trip count
-                        float4 nxt[4];
-                        if (base + 256 <= nq) load_group_full(row, base + 128, nxt);
-                        else if (base + 128 < nq) load_group(row, base + 128, nxt);
-                        else if (row_next) load_group(row_next, 0, nxt);
                         const int j = base + lane;
                         // residual rows (EXACT only): same offsets as the value rows, in the e_lo matrix
                         const float *lo_i = EXACT ? reinterpret_cast<const float *>(row + j) + lo_delta : nullptr;
                         const float *lo_c = EXACT ? lo_c_row + 4 * j : nullptr;
                         if (base + 128 <= nq) {                           // full group: no predicates
-                            accumulate4<TR, RULE, EXACT>(a, cur[0], s_e4[j], s_b4[j], p.psc, lo_i, lo_c);
-                            accumulate4<TR, RULE, EXACT>(a, cur[1], s_e4[j + 32], s_b4[j + 32], p.psc, lo_i + 128, lo_c + 128);
-                            accumulate4<TR, RULE, EXACT>(a, cur[2], s_e4[j + 64], s_b4[j + 64], p.psc, lo_i + 256, lo_c + 256);
-                            accumulate4<TR, RULE, EXACT>(a, cur[3], s_e4[j + 96], s_b4[j + 96], p.psc, lo_i + 384, lo_c + 384);
-                        } else {
+                            // (1) differences: the only consumers of the loaded values -> their registers are free
+                            const Diff4 d0 = diff4<EXACT>(cur[0], s_e4[j]);
+                            const Diff4 d1 = diff4<EXACT>(cur[1], s_e4[j + 32]);
+                            const Diff4 d2 = diff4<EXACT>(cur[2], s_e4[j + 64]);
+                            const Diff4 d3 = diff4<EXACT>(cur[3], s_e4[j + 96]);
+                            // (2) next group (or the next row's first group) straight into the same registers:
+                            //     no second buffer, no register copies, one group in flight during the math below
+                            if (base + 256 <= nq) load_group_full(row, base + 128, cur);
+                            else if (base + 128 < nq) load_group(row, base + 128, cur);
+                            else if (row_next) load_group(row_next, 0, cur);
+                            // (3) transform + accumulate
+                            accumulate_diff<TR, RULE, EXACT>(a, d0, s_b4[j], p.psc, lo_i, lo_c);
+                            accumulate_diff<TR, RULE, EXACT>(a, d1, s_b4[j + 32], p.psc, lo_i + 128, lo_c + 128);
+                            accumulate_diff<TR, RULE, EXACT>(a, d2, s_b4[j + 64], p.psc, lo_i + 256, lo_c + 256);
+                            accumulate_diff<TR, RULE, EXACT>(a, d3, s_b4[j + 96], p.psc, lo_i + 384, lo_c + 384);
+                        } else {                                          // ragged last group of the row
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 if (j + 32 * k < nq)
                                     accumulate4<TR, RULE, EXACT>(a, cur[k], s_e4[j + 32 * k], s_b4[j + 32 * k], p.psc,
                                                                  lo_i + 128 * k, lo_c + 128 * k);
+                            if (row_next) load_group(row_next, 0, cur);   // base + 128 >= nq here
                         }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
                     }
                     const int64_t i = s_ix[n];
                     float s1 = (a.s1[0].x + a.s1[0].y) + (a.s1[1].x + a.s1[1].y);
