@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libvelo_b200.so")
+LIB_PATH = os.environ.get("VELO_B200_LIB") or os.path.join(_PKG, "libvelo_b200.so")   # override: tuning builds only
 
 LINEAR, SQRT, LOG10 = 0, 1, 2
 RULE_FULL, RULE_PARTIAL = 0, 1

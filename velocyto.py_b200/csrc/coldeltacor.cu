@@ -19,7 +19,13 @@
 
 namespace velo {
 
-constexpr int kThreads = 512;            // 16 warps, 1 CTA / SM (shared memory bound)
+// 32 warps per SM (1 CTA / SM, shared-memory bound): the random-row gather is latency-bound, and bandwidth grows with the
+// number of row streams in flight -- measured 6.3 / 6.8 / 7.0 / 7.5 / 7.5 TB/s at 512 / 640 / 768 / 896 / 1024 threads
+// (profiles/r1_k1_ncu_v4.md).  64 registers per thread at 1024 threads: the single-buffer stream loop fits.
+#ifndef VELO_K1_THREADS
+#define VELO_K1_THREADS 1024
+#endif
+constexpr int kThreads = VELO_K1_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxChunk = 4096;          // neighbours handled per pass (accumulators + indices in smem)
 
