@@ -25,8 +25,14 @@ namespace velo {
 #ifndef VELO_K1_THREADS
 #define VELO_K1_THREADS 1024
 #endif
-constexpr int kThreads = VELO_K1_THREADS;
-constexpr int kWarps = kThreads / 32;
+#ifndef VELO_K1_THREADS_EXACT
+#define VELO_K1_THREADS_EXACT 768       // the tie-resolving variants need ~80 registers: 24 warps
+#endif
+template <bool EXACT>
+struct K1Cfg {
+    static constexpr int threads = EXACT ? VELO_K1_THREADS_EXACT : VELO_K1_THREADS;
+    static constexpr int warps = threads / 32;
+};
 constexpr int kMaxChunk = 4096;          // neighbours handled per pass (accumulators + indices in smem)
 
 struct CorrParams {
@@ -70,8 +76,14 @@ __device__ __forceinline__ float transform_diff(float t, float psc)
     }
 }
 
-struct Acc4 {                // 4-way interleaved partial sums, kept as two fp32x2 pairs each
-    float2 s1[2], s2[2], s3[2];
+// interleaved partial sums kept as fp32x2 pairs: 2 pairs (4-way) for one row per warp, 1 pair (2-way) when a warp
+// carries two rows at once (register budget)
+#ifndef VELO_K1_TWOROWS
+#define VELO_K1_TWOROWS 1
+#endif
+constexpr int kAccPairs = VELO_K1_TWOROWS ? 1 : 2;
+struct Acc4 {
+    float2 s1[kAccPairs], s2[kAccPairs], s3[kAccPairs];
 };
 
 // EXACT: the matrix came from fp64 data and carries fp32 residuals (e64 = e32 + lo).  Two DIFFERENT fp64 values
@@ -113,8 +125,9 @@ __device__ __forceinline__ void accumulate_diff(Acc4 &a, const Diff4 d, const fl
     const float2 A01 = make_float2(transform_diff<TR, RULE>(t0, psc), transform_diff<TR, RULE>(t1, psc));
     const float2 A23 = make_float2(transform_diff<TR, RULE>(t2, psc), transform_diff<TR, RULE>(t3, psc));
     // packed accumulation: three FADD2/FFMA2 per element pair instead of six scalar operations
+    constexpr int hi = kAccPairs - 1;
     a.s1[0] = add2(a.s1[0], A01); a.s2[0] = fma2(A01, A01, a.s2[0]); a.s3[0] = fma2(A01, make_float2(b.x, b.y), a.s3[0]);
-    a.s1[1] = add2(a.s1[1], A23); a.s2[1] = fma2(A23, A23, a.s2[1]); a.s3[1] = fma2(A23, make_float2(b.z, b.w), a.s3[1]);
+    a.s1[hi] = add2(a.s1[hi], A23); a.s2[hi] = fma2(A23, A23, a.s2[hi]); a.s3[hi] = fma2(A23, make_float2(b.z, b.w), a.s3[hi]);
 }
 
 template <int TR, int RULE, bool EXACT>
@@ -124,8 +137,10 @@ __device__ __forceinline__ void accumulate4(Acc4 &a, const float4 v, const float
     accumulate_diff<TR, RULE, EXACT>(a, diff4<EXACT>(v, ec), b, psc, lo_i, lo_c);
 }
 template <int TR, int RULE, bool EXACT>
-__global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
+__global__ void __launch_bounds__(K1Cfg<EXACT>::threads, 1) k_coldeltacor(const CorrParams p)
 {
+    constexpr int kThreads = K1Cfg<EXACT>::threads;
+    constexpr int kWarps = K1Cfg<EXACT>::warps;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_e = reinterpret_cast<float *>(smem_raw);
     float *s_b = s_e + p.Gs;
@@ -239,6 +254,97 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                 const ptrdiff_t lo_delta =                                                 // floats, between the two matrices
                     EXACT ? (reinterpret_cast<intptr_t>(p.e_lo) - reinterpret_cast<intptr_t>(p.e_cm)) / 4 : 0;
                 const float *lo_c_row = EXACT ? p.e_lo + cg * p.ld + g0 : nullptr;
+#if VELO_K1_TWOROWS
+                // Two neighbour rows per warp (pairs n, n + kWarps): every shared-memory read of e_c / b_c serves both
+                // rows, halving the L1TEX load that v4 found at 87 % (8 B of shared memory per 4 B of HBM).  Each row
+                // contributes two 128-bit loads per lane and trip, so registers and bytes in flight stay as before.
+                auto finish_row = [&](int n, const Acc4 &a) {
+                    const int64_t i = s_ix[n];
+                    float s1 = a.s1[0].x + a.s1[0].y, s2 = a.s2[0].x + a.s2[0].y, s3 = a.s3[0].x + a.s3[0].y;
+                    if (lane < (gl & 3)) {                               // ragged tail (G % 4 genes of the last slab)
+                        const int k = (nq << 2) + lane;
+                        const float v = __ldg(p.e_cm + i * p.ld + g0 + k);
+                        float t = v - s_e[k];
+                        if (EXACT && t == 0.0f && v != 0.0f)
+                            t = __ldg(p.e_lo + i * p.ld + g0 + k) - __ldg(lo_c_row + k);
+                        const float A = transform_diff<TR, RULE>(t, p.psc);
+                        s1 += A;
+                        s2 = fmaf(A, A, s2);
+                        s3 = fmaf(A, s_b[k], s3);
+                    }
+                    s1 = warp_sum(s1);
+                    s2 = warp_sum(s2);
+                    s3 = warp_sum(s3);
+                    if (lane == 0) {                                      // slabs are sequential -> deterministic order
+                        s_acc[n] += s1;
+                        s_acc[Mc + n] += s2;
+                        s_acc[2 * Mc + n] += s3;
+                    }
+                };
+                float4 cur[4];                                            // [0],[1]: row A at j, j+32; [2],[3]: row B
+                auto load_pair = [&](const float4 *ra, const float4 *rb, int base) {
+                    const int j0 = base + lane, j1 = j0 + 32;
+                    if (base + 64 <= nq) {
+                        cur[0] = ldg_stream_f4(ra + j0);
+                        cur[1] = ldg_stream_f4(ra + j1);
+                        cur[2] = ldg_stream_f4(rb + j0);
+                        cur[3] = ldg_stream_f4(rb + j1);
+                    } else {
+                        if (j0 < nq) { cur[0] = ldg_stream_f4(ra + j0); cur[2] = ldg_stream_f4(rb + j0); }
+                        if (j1 < nq) { cur[1] = ldg_stream_f4(ra + j1); cur[3] = ldg_stream_f4(rb + j1); }
+                    }
+                };
+                int nA = warp;
+                const float4 *rowA = nullptr, *rowB = nullptr;
+                if (nA < mc) {
+                    rowA = row_of(nA);
+                    rowB = nA + kWarps < mc ? row_of(nA + kWarps) : rowA;   // odd tail: B mirrors A (L2 hit), result unused
+                    load_pair(rowA, rowB, 0);
+                }
+                while (nA < mc) {
+                    const int nB = nA + kWarps;
+                    const bool hasB = nB < mc;
+                    const int nA2 = nA + 2 * kWarps;
+                    const float4 *rowA2 = nA2 < mc ? row_of(nA2) : nullptr;
+                    const float4 *rowB2 = nA2 + kWarps < mc ? row_of(nA2 + kWarps) : rowA2;
+                    Acc4 aA, aB;
+                    aA.s1[0] = aA.s2[0] = aA.s3[0] = make_float2(0.0f, 0.0f);
+                    aB.s1[0] = aB.s2[0] = aB.s3[0] = make_float2(0.0f, 0.0f);
+                    for (int base = 0; base < nq; base += 64) {           // warp-uniform trip count
+                        const int j = base + lane;
+                        const float *loA = EXACT ? reinterpret_cast<const float *>(rowA + j) + lo_delta : nullptr;
+                        const float *loB = EXACT ? reinterpret_cast<const float *>(rowB + j) + lo_delta : nullptr;
+                        const float *lo_c = EXACT ? lo_c_row + 4 * j : nullptr;
+                        if (base + 64 <= nq) {
+                            const float4 ec0 = s_e4[j], ec1 = s_e4[j + 32];
+                            const Diff4 dA0 = diff4<EXACT>(cur[0], ec0), dA1 = diff4<EXACT>(cur[1], ec1);
+                            const Diff4 dB0 = diff4<EXACT>(cur[2], ec0), dB1 = diff4<EXACT>(cur[3], ec1);
+                            if (base + 64 < nq) load_pair(rowA, rowB, base + 64);
+                            else if (rowA2) load_pair(rowA2, rowB2, 0);
+                            const float4 b0 = s_b4[j], b1 = s_b4[j + 32];
+                            accumulate_diff<TR, RULE, EXACT>(aA, dA0, b0, p.psc, loA, lo_c);
+                            accumulate_diff<TR, RULE, EXACT>(aB, dB0, b0, p.psc, loB, lo_c);
+                            accumulate_diff<TR, RULE, EXACT>(aA, dA1, b1, p.psc, loA + 128, lo_c + 128);
+                            accumulate_diff<TR, RULE, EXACT>(aB, dB1, b1, p.psc, loB + 128, lo_c + 128);
+                        } else {                                          // ragged last group of the row
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                if (j + 32 * k < nq) {
+                                    const float4 ec = s_e4[j + 32 * k], bb = s_b4[j + 32 * k];
+                                    accumulate4<TR, RULE, EXACT>(aA, cur[k], ec, bb, p.psc, loA + 128 * k, lo_c + 128 * k);
+                                    accumulate4<TR, RULE, EXACT>(aB, cur[2 + k], ec, bb, p.psc, loB + 128 * k, lo_c + 128 * k);
+                                }
+                            if (rowA2) load_pair(rowA2, rowB2, 0);         // base + 64 >= nq here
+                        }
+                    }
+                    finish_row(nA, aA);
+                    if (hasB) finish_row(nB, aB);
+                    nA = nA2;
+                    rowA = rowA2;
+                    rowB = rowB2;
+                }
+            }
+#else
                 int n = warp;
                 const float4 *row = nullptr;
                 float4 cur[4];
@@ -310,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_coldeltacor(const CorrParams p)
                     row = row_next;
                 }
             }
+#endif
             __syncthreads();
             // finalise this chunk of neighbours (fp64: a handful of operations per pair)
             for (int t = tid; t < mc; t += kThreads) {
@@ -402,7 +509,7 @@ static int launch_corr_impl(const CorrParams &p, int grid, size_t smem, cudaStre
 {
     VELO_CUDA_TRY(cudaFuncSetAttribute(k_coldeltacor<TR, RULE, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    k_coldeltacor<TR, RULE, EXACT><<<grid, kThreads, smem, st>>>(p);
+    k_coldeltacor<TR, RULE, EXACT><<<grid, K1Cfg<EXACT>::threads, smem, st>>>(p);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }
