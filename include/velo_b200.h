@@ -152,6 +152,17 @@ int velo_dev_coldeltacor_ex(int transform, int rule,
                             int64_t G, int64_t C, int64_t c0, int64_t nc, int64_t m,
                             double psc, velo_stream_t stream);
 
+/* K2g: the all-pairs LINEAR variant (x_colDeltaCor, speedboosted.pyx:13-87; `_colDeltaCor` :542-550) on the tensor
+ * cores: out[r * out_ld + i] = pearson_g(e[i, g] - e[c0 + r, g], d[r, g]) for every target i in [0, C), from the two
+ * products P = B X^T and Q = X X^T over the gene axis (bf16 hi/lo split operands, tcgen05.mma, fp32 block sums drained
+ * from TMEM every 64 genes; DESIGN.md "K2g").  Self pairs and coincident cells give NaN like the reference.
+ * Scratch (velo_coldeltacor_tc_workspace_bytes) comes from the stream-ordered pool.  dbgP/dbgQ: optional nc x out_ld
+ * raw products for diagnostics (both NULL in production). */
+int    velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int64_t ld, const float *stats,
+                               float *out, int64_t out_ld, int64_t G, int64_t C, int64_t c0, int64_t nc,
+                               float *dbgP, float *dbgQ, velo_stream_t stream);
+size_t velo_coldeltacor_tc_workspace_bytes(int64_t G, int64_t C, int64_t nc);
+
 /* rm[(c0 + r) * C + i] += out[r, n]  (dense adapter for small C; fp64 atomics so that
  * duplicated indices accumulate as in the reference, speedboosted.pyx:336) */
 int velo_dev_scatter_dense(const float *out, int64_t out_ld, const int32_t *ixs, int64_t ixs_ld,

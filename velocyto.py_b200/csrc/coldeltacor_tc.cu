@@ -1,0 +1,569 @@
+// K2g -- the all-pairs LINEAR correlation x_colDeltaCor (speedboosted.pyx:13-87) on the 5th-generation tensor
+// cores.  It is the only GEMM-shaped member of the colDeltaCor family (SURVEY 8d, row "K2g"): with
+//     x_c = e_c - gene_mean - mean_g(e_c - gene_mean)     (A = e_i - e_c is invariant under a per-gene shift)
+//     b_c = d_c - mean_g(d_c)
+// the reference's per-pair sums (pyx:30-78) collapse to two matrix products over the gene axis
+//     sum_g (A - mean A) * b       =  P[c,i] - P[c,c]              P = B X^T
+//     sum_g (A - mean A)^2         =  |x_i|^2 + |x_c|^2 - 2 Q[c,i]  Q = X X^T
+//     corr[c,i] = (P[c,i] - P[c,c]) / sqrt((|x_i|^2 + |x_c|^2 - 2 Q[c,i]) * |b_c|^2)
+//
+// Precision (the contract is 1e-5 on the transition probabilities, i.e. ~5e-7 absolute on corr):
+//   * every operand row is scaled by a power of two (max |x| * s in [2^13, 2^14)) and split x * s = hi + lo into two
+//     fp16 matrices: 22 significant bits relative to the row maximum (a bf16 pair would give 16 and, measured on
+//     the host, corr errors of 1e-6 at 500 genes; the fp16 pair gives 2e-8); hi*hi + hi*lo + lo*hi are three
+//     `tcgen05.mma.kind::f16` per product and gene step, the dropped lo*lo term is 2^-24 of the product;
+//   * the tensor core accumulates in fp32 WITHOUT round-to-nearest; over 30k genes that bias would reach 1e-4.
+//     The TMEM accumulators therefore only ever hold the partial sum of ONE 64-gene block (12 accumulations);
+//     eight epilogue warps drain them (tcgen05.ld) into fp32 running sums in registers (round-to-nearest adds)
+//     while the MMAs of the next block run into the other TMEM buffer.
+//
+// One CTA = one 128 cells x 128 targets tile of pairs; warp 0 = TMA producer (six 128 x 64 bf16 operand tiles per
+// gene block, SWIZZLE_128B boxes), warp 1 = MMA issuer (one thread, 24 MMAs 128x128x16 per gene block, accumulators
+// P and Q in TMEM, two buffers = all 512 columns), warps 2..9 = drain + final epilogue.  CTAs are rasterised in
+// groups of 16 cell blocks so that the ~148 tiles in flight share their operand rows through L2.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "velo_common.cuh"
+
+namespace velo {
+namespace tc {
+
+constexpr int kTM = 128, kTN = 128, kBK = 64;            // tile; kBK fp16 = one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr uint32_t kTileBytes = 128u * kBK * 2u;         // 16 KB per operand tile
+constexpr uint32_t kStageBytes = 6u * kTileBytes;        // Bh_I, Bl_I, Xh_I, Xl_I, Xh_J, Xl_J
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);           // 320
+constexpr uint32_t kTmemCols = 512;                      // 2 buffers x (P: 128 cols, Q: 128 cols)
+constexpr int kRasterGroup = 16;
+constexpr int kEpiPitch = 129;                           // fp32 row pitch of the parked sums (2 x 128 x 129 x 4 B = 129 KB)
+constexpr size_t kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 128 /*barriers*/;
+
+struct TcParams {
+    const double *qd;       // C   : |x_c|^2
+    const double *pcc;      // nc  : P[c,c]
+    const float *isx;       // C   : 1 / (power-of-two scale of operand row x_c)
+    const float *isb;       // nc  : 1 / (scale of operand row b_c)
+    const float *stats;     // nc x 2 (mean_g d, sum_g (d - mean)^2)  -- velo_dev_cell_stats
+    float *out;             // nc x out_ld
+    float *dbgP, *dbgQ;     // optional raw products (nc x out_ld), NULL in production
+    int64_t out_ld, C, c0, nc;
+    int nkb;                // gene blocks of 64
+    int nI, nJ;             // tile counts (cells, targets)
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("k_coldeltacor_tc: barrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *tm, int32_t x, int32_t y,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 x fp16 -> fp32, 128 x 128 x 16
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version [46,48) = 1,
+//  layout_type [61,64) = 2)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
+{
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024u >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (InstrDescriptor): c_format F32 [4,6) = 1, a/b_format F16 [7,10),[10,13) = 0, K-major A and B,
+// n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (static_cast<uint32_t>(kTN >> 3) << 17) | (static_cast<uint32_t>(kTM >> 4) << 24);
+
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane of its warp's quarter)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+k_coldeltacor_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;              // SWIZZLE_128B tiles: 1024-byte aligned
+    uint8_t *aligned = smem_raw + (base - raw_addr);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aligned + kStages * kStageBytes);
+    uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile of this CTA: groups of kRasterGroup cell blocks, targets fastest inside a group
+    int ti, tj;
+    {
+        const int64_t t = blockIdx.x;
+        const int64_t per_group = static_cast<int64_t>(kRasterGroup) * p.nJ;
+        const int g = static_cast<int>(t / per_group);
+        const int r = static_cast<int>(t - g * per_group);
+        const int gsz = min(kRasterGroup, p.nI - g * kRasterGroup);
+        ti = g * kRasterGroup + r % gsz;
+        tj = r / gsz;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], kEpiWarps);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {   // TMEM allocation: one full warp, which also owns the deallocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int32_t rowB = ti * kTM;                                   // local cell rows of B
+            const int32_t rowI = static_cast<int32_t>(p.c0) + ti * kTM;      // the same cells in X
+            const int32_t rowJ = tj * kTN;                                   // targets in X
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait_bounded(&empty[s], ph ^ 1);                        // slot free (passes at once on first use)
+                mbar_expect_tx(&full[s], kStageBytes);
+                const uint32_t dst = base + s * kStageBytes;
+                const int32_t g = kb * kBK;
+                tma_load_2d(dst + 0 * kTileBytes, &tmBh, g, rowB, &full[s]);
+                tma_load_2d(dst + 1 * kTileBytes, &tmBl, g, rowB, &full[s]);
+                tma_load_2d(dst + 2 * kTileBytes, &tmXh, g, rowI, &full[s]);
+                tma_load_2d(dst + 3 * kTileBytes, &tmXl, g, rowI, &full[s]);
+                tma_load_2d(dst + 4 * kTileBytes, &tmXh, g, rowJ, &full[s]);
+                tma_load_2d(dst + 5 * kTileBytes, &tmXl, g, rowJ, &full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                const int b = kb & 1;
+                const uint32_t bph = (kb >> 1) & 1;
+                mbar_wait_bounded(&tempty[b], bph ^ 1);                      // accumulator buffer drained
+                mbar_wait_bounded(&full[s], ph);                             // operands landed
+                tcgen05_fence_after();
+                const uint64_t d0 = make_smem_desc(base + s * kStageBytes);      // tile t, gene step k: + (t * 16 KB + k * 32 B) >> 4
+                const uint32_t dP = tmem_base + b * 256, dQ = dP + 128;
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t ko = static_cast<uint64_t>(k * 2);            // 16 fp16 = 32 bytes along the swizzled row
+                    const uint64_t aBh = d0 + (0 * (kTileBytes >> 4) + ko), aBl = d0 + (1 * (kTileBytes >> 4) + ko);
+                    const uint64_t aXh = d0 + (2 * (kTileBytes >> 4) + ko), aXl = d0 + (3 * (kTileBytes >> 4) + ko);
+                    const uint64_t bXh = d0 + (4 * (kTileBytes >> 4) + ko), bXl = d0 + (5 * (kTileBytes >> 4) + ko);
+                    umma_f16(dP, aBh, bXh, kIdesc, k > 0);                   // first MMA of the block overwrites
+                    umma_f16(dP, aBh, bXl, kIdesc, 1);
+                    umma_f16(dP, aBl, bXh, kIdesc, 1);
+                    umma_f16(dQ, aXh, bXh, kIdesc, k > 0);
+                    umma_f16(dQ, aXh, bXl, kIdesc, 1);
+                    umma_f16(dQ, aXl, bXh, kIdesc, 1);
+                }
+                tcgen05_commit(&empty[s]);                                   // smem slot reusable when these MMAs retire
+                tcgen05_commit(&tfull[b]);                                   // ... and the block sums are in TMEM
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== drain + epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., columns 64*h.. =====
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        float accP[64], accQ[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) accP[j] = accQ[j] = 0.f;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            const int b = kb & 1;
+            const uint32_t bph = (kb >> 1) & 1;
+            mbar_wait_bounded(&tfull[b], bph);
+            tcgen05_fence_after();
+            const uint32_t t0 = tmem_base + lane_base + b * 256 + h * 64;
+            float v[32];
+            tmem_ld32(t0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accP[j] += v[j];
+            tmem_ld32(t0 + 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accP[32 + j] += v[j];
+            tmem_ld32(t0 + 128, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accQ[j] += v[j];
+            tmem_ld32(t0 + 160, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accQ[32 + j] += v[j];
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[b]);
+        }
+        // final epilogue.  All MMAs have retired (last tfull), so the operand stages are free: park the sums there as
+        // two 128 x 129 fp32 tiles (odd row pitch: thread = row writes are conflict-free), then let each warp finish
+        // whole rows with lanes = consecutive targets (coalesced 128-byte stores).
+        float *sP = reinterpret_cast<float *>(aligned);
+        float *sQ = sP + kTM * kEpiPitch;
+        {
+            const int row = q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                sP[row * kEpiPitch + h * 64 + j] = accP[j];
+                sQ[row * kEpiPitch + h * 64 + j] = accQ[j];
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");       // the 8 epilogue warps only
+        const int ew = warp - 2;
+        for (int row = ew; row < kTM; row += kEpiWarps) {
+            const int64_t r = static_cast<int64_t>(ti) * kTM + row;
+            if (r >= p.nc) break;
+            const int64_t c = p.c0 + r;
+            const double qc = p.qd[c], pc = p.pcc[r], sb = p.stats[2 * r + 1];
+            const double isx_c = p.isx[c], isb_r = p.isb[r];
+#pragma unroll
+            for (int cc = 0; cc < kTN / 32; ++cc) {
+                const int col = cc * 32 + lane;
+                const int64_t i = static_cast<int64_t>(tj) * kTN + col;
+                if (i < p.C) {
+                    const double qi = p.qd[i], isx_i = p.isx[i];
+                    const double Pt = static_cast<double>(sP[row * kEpiPitch + col]) * (isb_r * isx_i);   // undo the
+                    const double Qt = static_cast<double>(sQ[row * kEpiPitch + col]) * (isx_c * isx_i);   // row scales
+                    const double dist2 = qc + qi - 2.0 * Qt;
+                    const double num = Pt - pc;
+                    // self pair and coincident cells: the reference has 0 * inf = NaN there (pyx:57-78); the
+                    // products resolve |x_i - x_c|^2 only down to ~1e-6 of the norms
+                    const bool degenerate = (i == c) || !(dist2 > 4e-6 * (qc + qi)) || !(sb > 0.0);
+                    p.out[r * p.out_ld + i] =
+                        degenerate ? __int_as_float(0x7fc00000) : static_cast<float>(num * rsqrt(dist2 * sb));
+                    if (p.dbgP) {
+                        p.dbgP[r * p.out_ld + i] = static_cast<float>(Pt);
+                        p.dbgQ[r * p.out_ld + i] = static_cast<float>(Qt);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- operand preparation ----------------------------------------------------------------------------------
+// gene means over all cells (any per-gene shift leaves e_i - e_c unchanged; the mean keeps the operands small so
+// that Q[c,i] is not dominated by the common expression profile): partial[y][g], fixed reduction order
+__global__ void k_tc_gene_partial(const float *e_cm, int64_t ld, int64_t G, int64_t C, int parts, double *partial)
+{
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int64_t per = (C + parts - 1) / parts;
+    const int64_t a = static_cast<int64_t>(blockIdx.y) * per, b = min(C, a + per);
+    double s = 0.0;
+    for (int64_t c = a; c < b; ++c) s += static_cast<double>(__ldg(e_cm + c * ld + g));
+    partial[static_cast<int64_t>(blockIdx.y) * G + g] = s;
+}
+__global__ void k_tc_gene_mean(const double *partial, int64_t G, int64_t C, int parts, float *mu)
+{
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double s = 0.0;
+    for (int y = 0; y < parts; ++y) s += partial[static_cast<int64_t>(y) * G + g];
+    mu[g] = static_cast<float>(s / static_cast<double>(C));
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();                      // sh reuse
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += sh[i];   // same order in every thread: deterministic
+    return t;
+}
+
+__device__ __forceinline__ float block_max(float v, float *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t = fmaxf(t, sh[i]);
+    return t;
+}
+// power-of-two s with bound * s in [2^13, 2^14): fp16 holds the scaled row without overflow, hi*hi sums over one
+// 64-gene block stay below 2^34
+__device__ __forceinline__ float pow2_scale(float bound)
+{
+    if (!(bound > 0.f) || !isfinite(bound)) return 1.f;
+    int e;
+    (void)frexpf(bound, &e);                  // bound = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, 14 - e);
+}
+
+// one CTA per cell: centred row x (fp32) -> scaled fp16 hi/lo; |x|^2; for local cells also b = d - mean, hi/lo, P[c,c]
+__global__ void __launch_bounds__(256)
+k_tc_prep(const float *e_cm, const float *d_cm, int64_t ld, const float *mu, const float *stats, int64_t G, int64_t Gp,
+          int64_t C, int64_t c0, int64_t nc, __half *Xh, __half *Xl, __half *Bh, __half *Bl, double *qd, double *pcc,
+          float *isx, float *isb)
+{
+    __shared__ double sh[8];
+    __shared__ float shf[8];
+    const int64_t c = blockIdx.x;
+    const float *erow = e_cm + c * ld;
+    const int64_t r = c - c0;
+    const bool local = r >= 0 && r < nc;
+    const float *drow = local ? d_cm + r * ld : nullptr;
+    const float dm = local ? stats[2 * r] : 0.f;
+    double s = 0.0;
+    float mx = 0.f, mb = 0.f;
+    for (int64_t g = threadIdx.x; g < G; g += blockDim.x) {
+        const float v = erow[g] - mu[g];
+        s += static_cast<double>(v);
+        mx = fmaxf(mx, fabsf(v));
+        if (local) mb = fmaxf(mb, fabsf(drow[g] - dm));
+    }
+    const float rm = static_cast<float>(block_sum(s, sh) / static_cast<double>(G));
+    const float sx = pow2_scale(block_max(mx, shf) + fabsf(rm));      // |x| <= max |e - mu| + |row mean|
+    const float sb = pow2_scale(block_max(mb, shf));
+    double q = 0.0, pc = 0.0;
+    for (int64_t g = threadIdx.x; g < Gp; g += blockDim.x) {
+        float x = 0.f, b = 0.f;
+        if (g < G) {
+            x = (erow[g] - mu[g]) - rm;
+            if (local) b = drow[g] - dm;
+        }
+        const float xs = x * sx;
+        const __half xh = __float2half_rn(xs);
+        const __half xl = __float2half_rn(xs - __half2float(xh));
+        Xh[c * Gp + g] = xh;
+        Xl[c * Gp + g] = xl;
+        q += static_cast<double>(x) * static_cast<double>(x);
+        if (local) {
+            const float bs = b * sb;
+            const __half bh = __float2half_rn(bs);
+            const __half bl = __float2half_rn(bs - __half2float(bh));
+            Bh[r * Gp + g] = bh;
+            Bl[r * Gp + g] = bl;
+            pc += static_cast<double>(x) * static_cast<double>(b);
+        }
+    }
+    q = block_sum(q, sh);
+    pc = block_sum(pc, sh);
+    if (threadIdx.x == 0) {
+        qd[c] = q;
+        isx[c] = 1.f / sx;
+        if (local) {
+            pcc[r] = pc;
+            isb[r] = 1.f / sb;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn *fn)
+{
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        VELO_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+        VELO_REQUIRE(sym != nullptr && qres == cudaDriverEntryPointSuccess,
+                     "coldeltacor_tc: the driver does not export cuTensorMapEncodeTiled");
+        cached = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    *fn = cached;
+    return VELO_OK;
+}
+
+// rows x Gp fp16 row-major matrix, boxes of 128 rows x 64 genes (128 bytes), SWIZZLE_128B, zero fill outside
+static int make_map(EncodeTiledFn enc, CUtensorMap *tm, const void *ptr, int64_t rows, int64_t Gp)
+{
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Gp), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Gp) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), 128u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VELO_REQUIRE(rc == CUDA_SUCCESS, "coldeltacor_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(rc));
+    return VELO_OK;
+}
+
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    ~Scratch()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    int alloc(size_t bytes, cudaStream_t s)
+    {
+        st = s;
+        VELO_CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 16, s));
+        return VELO_OK;
+    }
+};
+
+}  // namespace tc
+}  // namespace velo
+
+using namespace velo;
+
+extern "C" size_t velo_coldeltacor_tc_workspace_bytes(int64_t G, int64_t C, int64_t nc)
+{
+    const int64_t Gp = round_up(G, tc::kBK);
+    return static_cast<size_t>(2 * (C + nc) * Gp * 2 + (C + nc) * 12 + G * 4 + 64 * G * 8 + 4096);
+}
+
+extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int64_t ld, const float *stats, float *out,
+                                       int64_t out_ld, int64_t G, int64_t C, int64_t c0, int64_t nc, float *dbgP,
+                                       float *dbgQ, velo_stream_t stream)
+{
+    using namespace velo::tc;
+    VELO_REQUIRE(e_cm && d_cm && stats && out, "coldeltacor_tc: null pointer");
+    VELO_REQUIRE(G > 0 && C > 0 && nc >= 0 && c0 >= 0 && c0 + nc <= C, "coldeltacor_tc: bad sizes");
+    VELO_REQUIRE(ld >= G && out_ld >= C, "coldeltacor_tc: leading dimensions too small");
+    VELO_REQUIRE(C < (1LL << 31) - 256 && G < (1LL << 31) - 64, "coldeltacor_tc: sizes must fit int32 TMA coordinates");
+    VELO_REQUIRE((dbgP == nullptr) == (dbgQ == nullptr), "coldeltacor_tc: dbgP and dbgQ go together");
+    if (nc == 0) return VELO_OK;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int64_t Gp = round_up(G, kBK);
+    const int parts = 64;
+
+    Scratch xh, xl, bh, bl, qd, pcc, mu, partial, isx, isb;
+    if ((rc = xh.alloc(static_cast<size_t>(C * Gp) * 2, st))) return rc;
+    if ((rc = xl.alloc(static_cast<size_t>(C * Gp) * 2, st))) return rc;
+    if ((rc = bh.alloc(static_cast<size_t>(nc * Gp) * 2, st))) return rc;
+    if ((rc = bl.alloc(static_cast<size_t>(nc * Gp) * 2, st))) return rc;
+    if ((rc = qd.alloc(static_cast<size_t>(C) * 8, st))) return rc;
+    if ((rc = pcc.alloc(static_cast<size_t>(nc) * 8, st))) return rc;
+    if ((rc = mu.alloc(static_cast<size_t>(G) * 4, st))) return rc;
+    if ((rc = isx.alloc(static_cast<size_t>(C) * 4, st))) return rc;
+    if ((rc = isb.alloc(static_cast<size_t>(nc) * 4, st))) return rc;
+    if ((rc = partial.alloc(static_cast<size_t>(parts) * G * 8, st))) return rc;
+
+    {
+        dim3 grid(static_cast<unsigned>((G + 255) / 256), parts);
+        k_tc_gene_partial<<<grid, 256, 0, st>>>(e_cm, ld, G, C, parts, static_cast<double *>(partial.p));
+        VELO_LAUNCH_CHECK();
+        k_tc_gene_mean<<<static_cast<unsigned>((G + 255) / 256), 256, 0, st>>>(static_cast<double *>(partial.p), G, C,
+                                                                                parts, static_cast<float *>(mu.p));
+        VELO_LAUNCH_CHECK();
+        k_tc_prep<<<static_cast<unsigned>(C), 256, 0, st>>>(
+            e_cm, d_cm, ld, static_cast<float *>(mu.p), stats, G, Gp, C, c0, nc, static_cast<__half *>(xh.p),
+            static_cast<__half *>(xl.p), static_cast<__half *>(bh.p), static_cast<__half *>(bl.p),
+            static_cast<double *>(qd.p), static_cast<double *>(pcc.p), static_cast<float *>(isx.p),
+            static_cast<float *>(isb.p));
+        VELO_LAUNCH_CHECK();
+    }
+
+    EncodeTiledFn enc;
+    if ((rc = get_encode_fn(&enc))) return rc;
+    CUtensorMap tmXh, tmXl, tmBh, tmBl;
+    if ((rc = make_map(enc, &tmXh, xh.p, C, Gp))) return rc;
+    if ((rc = make_map(enc, &tmXl, xl.p, C, Gp))) return rc;
+    if ((rc = make_map(enc, &tmBh, bh.p, nc, Gp))) return rc;
+    if ((rc = make_map(enc, &tmBl, bl.p, nc, Gp))) return rc;
+
+    TcParams p;
+    p.qd = static_cast<double *>(qd.p);
+    p.pcc = static_cast<double *>(pcc.p);
+    p.isx = static_cast<float *>(isx.p);
+    p.isb = static_cast<float *>(isb.p);
+    p.stats = stats;
+    p.out = out;
+    p.dbgP = dbgP;
+    p.dbgQ = dbgQ;
+    p.out_ld = out_ld;
+    p.C = C;
+    p.c0 = c0;
+    p.nc = nc;
+    p.nkb = static_cast<int>(Gp / kBK);
+    p.nI = static_cast<int>((nc + kTM - 1) / kTM);
+    p.nJ = static_cast<int>((C + kTN - 1) / kTN);
+    const int64_t tiles = static_cast<int64_t>(p.nI) * p.nJ;
+    VELO_REQUIRE(tiles < (1LL << 31), "coldeltacor_tc: too many tiles for one launch");
+    VELO_REQUIRE(static_cast<size_t>(dp.smem_optin) >= kSmemBytes, "coldeltacor_tc: needs %zu bytes of shared memory",
+                 kSmemBytes);
+    VELO_CUDA_TRY(cudaFuncSetAttribute(k_coldeltacor_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kSmemBytes)));
+    k_coldeltacor_tc<<<static_cast<unsigned>(tiles), kThreads, kSmemBytes, st>>>(tmXh, tmXl, tmBh, tmBl, p);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}

@@ -172,6 +172,24 @@ def coldeltacor(e_cm: CellMajor, d_cm: CellMajor, ixs: Optional[torch.Tensor], t
     return out
 
 
+def coldeltacor_linear_tc(e_cm: CellMajor, d_cm: CellMajor, c0: int = 0, stats: Optional[torch.Tensor] = None,
+                          out: Optional[torch.Tensor] = None, debug: bool = False):
+    """All-pairs linear correlation on the tensor cores (K2g; ``x_colDeltaCor``, speedboosted.pyx:13-87):
+    ``out[r, i]`` for local cells ``c0 .. c0+nc`` against every cell.  ``debug=True`` also returns the raw
+    products ``(P, Q)``."""
+    nc, C, G = d_cm.C, e_cm.C, e_cm.G
+    assert d_cm.G == G and d_cm.ld == e_cm.ld
+    if stats is None:
+        stats = cell_stats(d_cm)
+    if out is None:
+        out = torch.empty((nc, C), dtype=torch.float32, device=e_cm.t.device)
+    P = torch.zeros_like(out) if debug else None
+    Q = torch.zeros_like(out) if debug else None
+    _cabi.call("velo_dev_coldeltacor_tc", e_cm.ptr, d_cm.ptr, e_cm.ld, stats.data_ptr(), out.data_ptr(), out.stride(0),
+               G, C, c0, nc, 0 if P is None else P.data_ptr(), 0 if Q is None else Q.data_ptr(), _stream_ptr())
+    return (out, P, Q) if debug else out
+
+
 def transition_prob(corr: torch.Tensor, ixs: Optional[torch.Tensor], sigma: float, c0: int = 0,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Compact ``exp(corr/sigma)`` row-normalised with self->0 / NaN->1 patches (analysis.py:1604-1612,1697-1698)."""
