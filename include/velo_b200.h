@@ -135,7 +135,7 @@ int velo_dev_cell_stats(const float *d_cm, int64_t ld, int64_t G, int64_t nc,
  * e_cm : C x ld cell-major fp32 (ALL cells: neighbours may be any cell)
  * d_cm : nc x ld (rows of the local cells only), stats from velo_dev_cell_stats
  * rule : VELO_RULE_PARTIAL or VELO_RULE_FULL (zero rule of the variant)
- * Workspace-free.  One launch. */
+ * Workspace-free, one launch -- except the all-pairs linear case, which runs on the tensor cores (K2g below). */
 int velo_dev_coldeltacor(int transform, int rule,
                          const float *e_cm, const float *d_cm, int64_t ld,
                          const float *stats, const int32_t *ixs, int64_t ixs_ld,
@@ -162,6 +162,10 @@ int    velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int64_t ld,
                                float *out, int64_t out_ld, int64_t G, int64_t C, int64_t c0, int64_t nc,
                                float *dbgP, float *dbgQ, velo_stream_t stream);
 size_t velo_coldeltacor_tc_workspace_bytes(int64_t G, int64_t C, int64_t nc);
+/* velo_dev_coldeltacor{,_ex} route (ixs == NULL, VELO_LINEAR) to K2g; 0 switches back to the fp32 kernel K2
+ * (A/B measurements, or when the K2g scratch of 8 bytes per matrix element does not fit).  Default 1. */
+void   velo_set_tensor_cores(int enable);
+int    velo_get_tensor_cores(void);
 
 /* rm[(c0 + r) * C + i] += out[r, n]  (dense adapter for small C; fp64 atomics so that
  * duplicated indices accumulate as in the reference, speedboosted.pyx:336) */

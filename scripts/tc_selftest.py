@@ -97,8 +97,11 @@ def run_time(G, C):
     D.t[:, :G] = torch.from_numpy(rng.normal(size=(C, G)).astype(np.float32)).cuda()
     stats = dev.cell_stats(D)
     out = torch.empty((C, C), dtype=torch.float32, device="cuda")
+    from velocyto_b200 import _cabi
+    lib = _cabi.load()
     for name, fn in (("K2g tensor", lambda: dev.coldeltacor_linear_tc(E, D, stats=stats, out=out)),
                      ("K2 fp32  ", lambda: dev.coldeltacor(E, D, None, "linear", 0.0, stats=stats, out=out))):
+        lib.velo_set_tensor_cores(0 if name.startswith("K2 ") else 1)
         fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -111,7 +114,27 @@ def run_time(G, C):
         ms = a.elapsed_time(b) / reps
         pg = G * C * C
         print(f"[time G={G} C={C}] {name}: {ms:9.2f} ms   {pg / ms / 1e9:8.2f} T pair-gene/s"
-              f"   (tensor flop rate if 12 flop/pair-gene: {12 * pg / ms / 1e12:7.1f} TFLOP/s)")
+              f"   ({12 * pg / ms / 1e12:7.3f} PFLOP/s at 12 flop per pair-gene)")
+    lib.velo_set_tensor_cores(1)
+
+
+def run_bias(G, C):
+    """Accumulation bias of long tensor-core sums: drain the TMEM block sums every D 64-gene groups."""
+    e, d, c0, nc = make(G, C, 3)
+    E = dev.CellMajor.from_gene_major(e)
+    D = dev.CellMajor.from_gene_major(d)
+    Pw, Qw, cw = reference(e, d, 0, C)
+    ok = ~np.isnan(cw)
+    big = np.abs(Qw) > 0.05 * np.abs(Qw).max()
+    for dg in (1, 2, 4, 16, 64, 4096):
+        os.environ["VELO_TC_DRAIN_GROUPS"] = str(dg)
+        out, P, Q = dev.coldeltacor_linear_tc(E, D, debug=True)
+        torch.cuda.synchronize()
+        P, Q, out = (t.cpu().numpy().astype(np.float64) for t in (P, Q, out))
+        relQ = (Q - Qw)[big] / Qw[big]
+        print(f"[bias G={G} C={C}] drain every {dg:4d} x 64 genes: Q rel err mean {relQ.mean():+.3e} rms {relQ.std():.3e}"
+              f"   |P| err/max {np.abs(P - Pw).max() / np.abs(Pw).max():.3e}   corr max abs err {np.abs(out - cw)[ok].max():.3e}")
+    os.environ.pop("VELO_TC_DRAIN_GROUPS")
 
 
 if __name__ == "__main__":
@@ -124,3 +147,5 @@ if __name__ == "__main__":
         run_onehot()
     elif mode == "time":
         run_time(int(sys.argv[2]), int(sys.argv[3]))
+    elif mode == "bias":
+        run_bias(int(sys.argv[2]), int(sys.argv[3]))

@@ -321,3 +321,85 @@ def test_empty_and_degenerate_shapes():
     assert one_cell.shape == (1, 1)
     with pytest.raises(VeloError):
         est.colDeltaCor(np.empty((0, 5)), np.empty((0, 5)))                                          # no genes at all
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K2g: the all-pairs linear variant on the tensor cores (csrc/coldeltacor_tc.cu)
+
+def _tc_inputs(G, C, seed):
+    """Genes with very different expression levels (the common profile must cancel in e_i - e_c) and a velocity
+    field correlated with the expression differences, so that correlations are not all ~0."""
+    rng = np.random.default_rng(seed)
+    level = rng.gamma(0.6, 2.0, G)[:, None] + 0.05
+    e = rng.gamma(2.0, 1.0, (G, C)) * level
+    e[rng.uniform(size=(G, C)) < 0.3] = 0.0
+    z = rng.normal(size=(G, C))
+    d = z + 0.5 * (e - e.mean(1, keepdims=True)) / (e.std(1, keepdims=True) + 1e-9)
+    return e.astype(np.float32).astype(np.float64), d.astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("G,C,c0,nc", [(3000, 700, 0, 700), (777, 333, 100, 200), (64, 128, 0, 128), (5, 9, 2, 4),
+                                       (4097, 130, 1, 129)])
+def test_tensor_core_linear_matches_oracle(oracle, G, C, c0, nc):
+    """x_colDeltaCor (speedboosted.pyx:13-87) via tcgen05: ragged gene blocks (G % 64 != 0), ragged tiles
+    (C % 128 != 0), a cell shard (c0, nc), and tiny shapes; 5e-7 absolute as for the other kernels."""
+    from velocyto_b200 import device as dev
+    e, d = _tc_inputs(G, C, G + C)
+    want = oracle.coldeltacor(e, d, None, "linear", 0.0)[c0:c0 + nc]
+    E, D = dev.CellMajor.from_gene_major(e), dev.CellMajor.from_gene_major(d[:, c0:c0 + nc])
+    got = dev.coldeltacor_linear_tc(E, D, c0=c0).cpu().numpy()
+    self_pair = np.zeros((nc, C), dtype=bool)
+    self_pair[np.arange(nc), c0 + np.arange(nc)] = True
+    assert np.isnan(got[self_pair]).all()                       # 0 * inf in the reference (probed: NaN)
+    assert not np.isnan(got[~self_pair]).any()
+    np.testing.assert_allclose(got[~self_pair], want[~self_pair], rtol=0, atol=5e-7)
+
+
+def test_tensor_core_linear_is_the_default_full_linear_path(oracle):
+    """estimation.colDeltaCor (host tier, dense fp64 output) runs K2g; switching the tensor cores off gives the fp32
+    kernel K2; both within tolerance of the oracle, K2g launches its own kernels."""
+    from velocyto_b200 import _cabi
+    import velocyto_b200.estimation as est
+    G, C = 2500, 300
+    e, d = _tc_inputs(G, C, 5)
+    want = oracle.coldeltacor(e, d, None, "linear", 0.0)
+    off = ~np.eye(C, dtype=bool)
+    lib = _cabi.load()
+    assert lib.velo_get_tensor_cores() == 1
+    got_tc = est.colDeltaCor(e, d)
+    try:
+        lib.velo_set_tensor_cores(0)
+        got_k2 = est.colDeltaCor(e, d)
+    finally:
+        lib.velo_set_tensor_cores(1)
+    np.testing.assert_allclose(got_tc[off], want[off], rtol=0, atol=5e-7)
+    # K2 keeps one fp32 FMA chain per sum over all genes: on expression levels this heavy-tailed it reaches ~1e-6
+    np.testing.assert_allclose(got_k2[off], want[off], rtol=0, atol=2e-6)
+    assert not np.array_equal(got_tc[off], got_k2[off])         # really two different kernels
+    assert np.abs(got_tc - want)[off].max() <= np.abs(got_k2 - want)[off].max()   # split-fp16 + block sums beat fp32 FMA chains
+
+
+def test_tensor_core_linear_degenerate_cells(oracle):
+    """Coincident cells (A == 0 everywhere) and constant velocity rows are 0 * inf = NaN in the reference."""
+    from velocyto_b200 import device as dev
+    G, C = 500, 140
+    e, d = _tc_inputs(G, C, 9)
+    e[:, 17] = e[:, 3]                                          # two identical cells
+    d[:, 50] = 0.25                                             # zero-variance velocity
+    want = oracle.coldeltacor(e, d, None, "linear", 0.0)
+    got = dev.coldeltacor_linear_tc(dev.CellMajor.from_gene_major(e), dev.CellMajor.from_gene_major(d)).cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=5e-7)
+
+
+def test_tensor_core_linear_transition_probabilities(oracle):
+    """The north-star bar: transition probabilities within 1e-5 relative of the reference path at 8000 genes."""
+    from velocyto_b200 import device as dev
+    G, C = 8000, 256
+    e, d = _tc_inputs(G, C, 21)
+    corr_want = oracle.patch_corrcoef(oracle.coldeltacor(e, d, None, "linear", 0.0))
+    tp_want = oracle.transition_prob(corr_want, np.ones((C, C)), 0.05)   # full mode: the mask keeps the self term
+    corr = dev.coldeltacor_linear_tc(dev.CellMajor.from_gene_major(e), dev.CellMajor.from_gene_major(d))
+    tp = dev.transition_prob(corr, None, 0.05).cpu().numpy()
+    np.testing.assert_allclose(tp, tp_want, rtol=1e-5, atol=0)

@@ -51,6 +51,8 @@ PROTOTYPES = {
                                        _i64, _i64, _i64, _i64, _i64, _dbl, _ptr]),
     "velo_dev_coldeltacor_tc": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "velo_coldeltacor_tc_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64]),
+    "velo_set_tensor_cores": (None, [_int]),
+    "velo_get_tensor_cores": (_int, []),
     "velo_dev_scatter_dense": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr]),
     "velo_dev_transition_prob": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _dbl, _ptr]),
     "velo_dev_fit_gammas": (_int, [_int, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _dbl, _dbl,

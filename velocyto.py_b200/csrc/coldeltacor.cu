@@ -564,6 +564,10 @@ extern "C" int velo_dev_coldeltacor_ex(int transform, int rule, const float *e_c
     VELO_REQUIRE(out_ld >= m, "coldeltacor: out_ld < m");
     VELO_REQUIRE(C < (1LL << 31), "coldeltacor: C must fit int32 indices");
     if (nc == 0 || m == 0) return VELO_OK;
+    // all-pairs linear: a pair of GEMMs over the gene axis -> tensor cores (K2g); the zero rules only concern the
+    // sqrt/log10 transforms, and a linear difference has no fp32 tie to resolve
+    if (ixs == nullptr && transform == VELO_LINEAR && velo_get_tensor_cores())
+        return velo_dev_coldeltacor_tc(e_cm, d_cm, ld, stats, out, out_ld, G, C, c0, nc, nullptr, nullptr, stream);
     // all-pairs with the full zero rule and no tie residuals: the register-tiled kernel K2 (compute-bound)
     if (ixs == nullptr && rule == VELO_RULE_FULL && e_lo_cm == nullptr)
         return coldeltacor_full_tiled(transform, e_cm, d_cm, ld, stats, out, out_ld, G, C, c0, nc, psc,

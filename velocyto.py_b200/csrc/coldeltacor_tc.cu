@@ -23,15 +23,25 @@
 // groups of 16 cell blocks so that the ~148 tiles in flight share their operand rows through L2.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "velo_common.cuh"
 
 namespace velo {
 namespace tc {
 
-constexpr int kTM = 128, kTN = 128, kBK = 64;            // tile; kBK fp16 = one 128-byte swizzle row
-constexpr int kStages = 2;
-constexpr uint32_t kTileBytes = 128u * kBK * 2u;         // 16 KB per operand tile
+constexpr int kTM = 128, kTN = 128;                      // tile of pairs per CTA
+constexpr int kGroup = 64;                               // genes per TMEM block sum (one drain)
+#ifndef VELO_TC_BK
+#define VELO_TC_BK 64
+#endif
+constexpr int kBK = VELO_TC_BK;                          // genes per pipeline stage: 64 (SWIZZLE_128B rows; 2 stages) or 32
+                                                         // (SWIZZLE_64B, 4 stages: measured 10 % slower)
+static_assert(kBK == 32 || kBK == 64, "kBK");
+constexpr int kStages = kBK == 64 ? 2 : 4;               // 192 KB of operand stages either way
+constexpr int kStagesPerGroup = kGroup / kBK;
+constexpr uint32_t kRowBytes = kBK * 2u;                 // one swizzle row
+constexpr uint32_t kTileBytes = 128u * kRowBytes;        // 8 / 16 KB per operand tile
 constexpr uint32_t kStageBytes = 6u * kTileBytes;        // Bh_I, Bl_I, Xh_I, Xl_I, Xh_J, Xl_J
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);           // 320
@@ -49,7 +59,8 @@ struct TcParams {
     float *out;             // nc x out_ld
     float *dbgP, *dbgQ;     // optional raw products (nc x out_ld), NULL in production
     int64_t out_ld, C, c0, nc;
-    int nkb;                // gene blocks of 64
+    int nkb;                // pipeline stages over the gene axis (Gp / kBK)
+    int drain_groups;       // 64-gene groups per TMEM drain (1 in production; > 1 only to measure the accumulation bias)
     int nI, nJ;             // tile counts (cells, targets)
 };
 
@@ -97,13 +108,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart
-// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version [46,48) = 1,
-//  layout_type [61,64) = 2)
+// shared-memory matrix descriptor, K-major, rows of one swizzle span (128 B: SWIZZLE_128B = 2, 64 B: SWIZZLE_64B = 4),
+// 8-row groups 8 * row bytes apart (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version [46,48) = 1, layout_type [61,64))
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
 {
-    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024u >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+    constexpr uint64_t layout = kBK == 64 ? 2ull : 4ull;
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) |
+           (static_cast<uint64_t>((8u * kRowBytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 // instruction descriptor (InstrDescriptor): c_format F32 [4,6) = 1, a/b_format F16 [7,10),[10,13) = 0, K-major A and B,
 // n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
@@ -202,15 +214,17 @@ k_coldeltacor_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
+            const int per_drain = p.drain_groups * kStagesPerGroup;              // stages per TMEM block sum
             for (int kb = 0; kb < p.nkb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
-                const int b = kb & 1;
-                const uint32_t bph = (kb >> 1) & 1;
-                mbar_wait_bounded(&tempty[b], bph ^ 1);                      // accumulator buffer drained
-                mbar_wait_bounded(&full[s], ph);                             // operands landed
+                const int dr = kb / per_drain, in_dr = kb - dr * per_drain;      // drain index, stage inside it
+                const int b = dr & 1;
+                const uint32_t bph = (dr >> 1) & 1;
+                if (in_dr == 0) mbar_wait_bounded(&tempty[b], bph ^ 1);          // accumulator buffer drained
+                mbar_wait_bounded(&full[s], ph);                                 // operands landed
                 tcgen05_fence_after();
-                const uint64_t d0 = make_smem_desc(base + s * kStageBytes);      // tile t, gene step k: + (t * 16 KB + k * 32 B) >> 4
+                const uint64_t d0 = make_smem_desc(base + s * kStageBytes);      // tile t, gene step k: + (t * tile + k * 32 B) >> 4
                 const uint32_t dP = tmem_base + b * 256, dQ = dP + 128;
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
@@ -218,15 +232,16 @@ k_coldeltacor_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
                     const uint64_t aBh = d0 + (0 * (kTileBytes >> 4) + ko), aBl = d0 + (1 * (kTileBytes >> 4) + ko);
                     const uint64_t aXh = d0 + (2 * (kTileBytes >> 4) + ko), aXl = d0 + (3 * (kTileBytes >> 4) + ko);
                     const uint64_t bXh = d0 + (4 * (kTileBytes >> 4) + ko), bXl = d0 + (5 * (kTileBytes >> 4) + ko);
-                    umma_f16(dP, aBh, bXh, kIdesc, k > 0);                   // first MMA of the block overwrites
+                    const uint32_t acc = (in_dr > 0 || k > 0) ? 1u : 0u;         // first MMA of a block sum overwrites
+                    umma_f16(dP, aBh, bXh, kIdesc, acc);
                     umma_f16(dP, aBh, bXl, kIdesc, 1);
                     umma_f16(dP, aBl, bXh, kIdesc, 1);
-                    umma_f16(dQ, aXh, bXh, kIdesc, k > 0);
+                    umma_f16(dQ, aXh, bXh, kIdesc, acc);
                     umma_f16(dQ, aXh, bXl, kIdesc, 1);
                     umma_f16(dQ, aXl, bXh, kIdesc, 1);
                 }
-                tcgen05_commit(&empty[s]);                                   // smem slot reusable when these MMAs retire
-                tcgen05_commit(&tfull[b]);                                   // ... and the block sums are in TMEM
+                tcgen05_commit(&empty[s]);                                       // smem slot reusable when these MMAs retire
+                if (in_dr == per_drain - 1 || kb == p.nkb - 1) tcgen05_commit(&tfull[b]);   // block sums are in TMEM
             }
         }
         __syncwarp();
@@ -238,9 +253,11 @@ k_coldeltacor_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 64; ++j) accP[j] = accQ[j] = 0.f;
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-            const int b = kb & 1;
-            const uint32_t bph = (kb >> 1) & 1;
+        const int per_drain = p.drain_groups * kStagesPerGroup;
+        const int ndrains = (p.nkb + per_drain - 1) / per_drain;
+        for (int dr = 0; dr < ndrains; ++dr) {
+            const int b = dr & 1;
+            const uint32_t bph = (dr >> 1) & 1;
             mbar_wait_bounded(&tfull[b], bph);
             tcgen05_fence_after();
             const uint32_t t0 = tmem_base + lane_base + b * 256 + h * 64;
@@ -313,6 +330,265 @@ k_coldeltacor_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     }
 }
 
+}  // namespace tc
+
+// ---- the two-CTA kernel (cta_group::2) ---------------------------------------------------------------------
+// The one-CTA kernel above is bound by the shared-memory port, not by the tensor pipe: per 64 genes its MMAs read
+// 24 x 8 KB of operands and TMA writes another 96 KB through the same 128 B/clk port (ncu: tensor pipe 70 % active,
+// l1tex tc wavefronts 70 %).  Here a CTA PAIR works on 128 cells x 256 targets with ONE M = 256 instruction stream:
+//   rows   0..127 of the A operand live in CTA 0 and are B rows  -> its TMEM accumulates P = B X^T
+//   rows 128..255 of the A operand live in CTA 1 and are X rows  -> its TMEM accumulates Q = X X^T
+//   the N = 256 target rows of X are staged half in each CTA (tcgen05.mma.cta_group::2 reads both halves)
+// Per CTA and 64 genes: operands 64 KB (was 96), MMA operand reads 12 x 8 KB (was 24 x 8 KB) for the same 1536 tensor
+// cycles; one 256-column accumulator per CTA, double buffered (512 TMEM columns), 128 running sums per epilogue
+// thread as before.  CTA 0 issues all MMAs; completion is multicast to both CTAs' barriers; the peer's TMA loads and
+// drain arrivals signal CTA 0's barriers through the cluster shared-memory window.
+namespace tc2 {
+constexpr int kTM = 128, kTN = 256, kBK = 64;
+constexpr int kStages = 3;
+constexpr uint32_t kTileBytes = 128u * kBK * 2u;         // 16 KB
+constexpr uint32_t kStageBytes = 4u * kTileBytes;        // A hi, A lo, target-half hi, target-half lo
+constexpr int kEpiPitch = 257;                           // parked sums: 128 x 257 fp32 = 129 KB per CTA
+constexpr size_t kSmemBytes = kStages * kStageBytes + 1024 + 128;
+constexpr uint32_t kIdesc = (1u << 4) | (static_cast<uint32_t>(256 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr)
+{
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+// TMA into this CTA's shared memory, completion bytes on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap *tm, int32_t x, int32_t y,
+                                                 uint32_t bar_cluster_addr)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once all MMAs issued so far have retired
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t *bar)
+{
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr)
+{
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024u >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::kThreads, 1)
+k_coldeltacor_tc2(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const tc::TcParams p)
+{
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t *aligned = smem_raw + (base - raw_addr);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aligned + kStages * kStageBytes);
+    uint64_t *full = bars, *empty = bars + kStages, *tfull = bars + 2 * kStages, *tempty = bars + 2 * kStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    int ti, tj;   // pair tile: 128 cells x 256 targets; groups of kRasterGroup cell blocks, targets fastest inside a group
+    {
+        const int64_t t = blockIdx.x >> 1;
+        const int64_t per_group = static_cast<int64_t>(kRasterGroup) * p.nJ;
+        const int g = static_cast<int>(t / per_group);
+        const int r = static_cast<int>(t - g * per_group);
+        const int gsz = min(kRasterGroup, p.nI - g * kRasterGroup);
+        ti = g * kRasterGroup + r % gsz;
+        tj = r / gsz;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);              // CTA 0's copy is the one in use: its producer's arrive.expect_tx
+            mbar_init(&empty[s], 1);             // multicast commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);             // multicast commit
+            mbar_init(&tempty[b], 2 * kEpiWarps);   // CTA 0's copy: the epilogue warps of both CTAs
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync();                              // barriers of BOTH CTAs initialised before any remote signal
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int per_drain = p.drain_groups;        // kBK == kGroup here: one stage per 64-gene group
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            const CUtensorMap *tmAh = rank ? &tmXh : &tmBh, *tmAl = rank ? &tmXl : &tmBl;
+            const int32_t rowA = rank ? static_cast<int32_t>(p.c0) + ti * kTM : ti * kTM;
+            const int32_t rowJ = tj * kTN + static_cast<int32_t>(rank) * 128;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait_bounded(&empty[s], ph ^ 1);
+                if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);    // this CTA's bytes and the peer's
+                const uint32_t leader_full = mapa(smem_u32(&full[s]), 0);
+                const uint32_t dst = base + s * kStageBytes;
+                const int32_t g = kb * kBK;
+                tma_load_2d_pair(dst + 0 * kTileBytes, tmAh, g, rowA, leader_full);
+                tma_load_2d_pair(dst + 1 * kTileBytes, tmAl, g, rowA, leader_full);
+                tma_load_2d_pair(dst + 2 * kTileBytes, &tmXh, g, rowJ, leader_full);
+                tma_load_2d_pair(dst + 3 * kTileBytes, &tmXl, g, rowJ, leader_full);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of CTA 0 drives both tensor cores =====
+        if (rank == 0 && lane == 0) {
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                const int dr = kb / per_drain, in_dr = kb - dr * per_drain;
+                const int b = dr & 1;
+                const uint32_t bph = (dr >> 1) & 1;
+                if (in_dr == 0) mbar_wait_bounded(&tempty[b], bph ^ 1);
+                mbar_wait_bounded(&full[s], ph);
+                tcgen05_fence_after();
+                const uint64_t d0 = make_smem_desc_sw128(base + s * kStageBytes);
+                const uint32_t dD = tmem_base + b * 256;
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t ko = static_cast<uint64_t>(k * 2);
+                    const uint64_t aH = d0 + ko, aL = d0 + ((kTileBytes >> 4) + ko);
+                    const uint64_t bH = d0 + (2 * (kTileBytes >> 4) + ko), bL = d0 + (3 * (kTileBytes >> 4) + ko);
+                    umma_f16_pair(dD, aH, bH, kIdesc, (in_dr > 0 || k > 0) ? 1u : 0u);
+                    umma_f16_pair(dD, aH, bL, kIdesc, 1);
+                    umma_f16_pair(dD, aL, bH, kIdesc, 1);
+                }
+                tcgen05_commit_pair(&empty[s]);
+                if (in_dr == per_drain - 1 || kb == p.nkb - 1) tcgen05_commit_pair(&tfull[b]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== drain: this CTA's accumulator (P in CTA 0, Q in CTA 1), lanes 32*(w%4).., columns 128*h.. =====
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        float acc[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        const int ndrains = (p.nkb + per_drain - 1) / per_drain;
+        for (int dr = 0; dr < ndrains; ++dr) {
+            const int b = dr & 1;
+            const uint32_t bph = (dr >> 1) & 1;
+            mbar_wait_bounded(&tfull[b], bph);
+            tcgen05_fence_after();
+            const uint32_t t0 = tmem_base + lane_base + b * 256 + h * 128;
+            float v[32];
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+                tmem_ld32(t0 + part * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[part * 32 + j] += v[j];
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tempty[b]), 0));
+        }
+        // park the sums in this CTA's (now idle) operand stages: 128 x 257 fp32
+        float *sS = reinterpret_cast<float *>(aligned);
+        const int row = q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sS[row * kEpiPitch + h * 128 + j] = acc[j];
+    }
+    cluster_sync();                              // both tiles parked and visible cluster-wide
+    if (warp >= 2) {
+        // CTA r finishes rows 64*r .. 64*r+63 of the pair tile: P from CTA 0's shared memory, Q from CTA 1's
+        const uint32_t sbase = smem_u32(aligned);
+        const uint32_t baseP = mapa(sbase, 0), baseQ = mapa(sbase, 1);
+        const int ew = warp - 2;
+        for (int rr = ew; rr < 64; rr += kEpiWarps) {
+            const int row = static_cast<int>(rank) * 64 + rr;
+            const int64_t r = static_cast<int64_t>(ti) * kTM + row;
+            if (r >= p.nc) break;
+            const int64_t c = p.c0 + r;
+            const double qc = p.qd[c], pc = p.pcc[r], sb = p.stats[2 * r + 1];
+            const double isx_c = p.isx[c], isb_r = p.isb[r];
+#pragma unroll
+            for (int cc = 0; cc < kTN / 32; ++cc) {
+                const int col = cc * 32 + lane;
+                const int64_t i = static_cast<int64_t>(tj) * kTN + col;
+                if (i < p.C) {
+                    const uint32_t off = static_cast<uint32_t>(row * kEpiPitch + col) * 4u;
+                    const double qi = p.qd[i], isx_i = p.isx[i];
+                    const double Pt = static_cast<double>(ld_cluster_f32(baseP + off)) * (isb_r * isx_i);
+                    const double Qt = static_cast<double>(ld_cluster_f32(baseQ + off)) * (isx_c * isx_i);
+                    const double dist2 = qc + qi - 2.0 * Qt;
+                    const double num = Pt - pc;
+                    const bool degenerate = (i == c) || !(dist2 > 4e-6 * (qc + qi)) || !(sb > 0.0);
+                    p.out[r * p.out_ld + i] =
+                        degenerate ? __int_as_float(0x7fc00000) : static_cast<float>(num * rsqrt(dist2 * sb));
+                    if (p.dbgP) {
+                        p.dbgP[r * p.out_ld + i] = static_cast<float>(Pt);
+                        p.dbgQ[r * p.out_ld + i] = static_cast<float>(Qt);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync();                              // nobody leaves while the peer still reads its shared memory
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+}  // namespace tc2
+
+namespace tc {
 // ---- operand preparation ----------------------------------------------------------------------------------
 // gene means over all cells (any per-gene shift leaves e_i - e_c unchanged; the mean keeps the operands small so
 // that Q[c,i] is not dominated by the common expression profile): partial[y][g], fixed reduction order
@@ -448,7 +724,7 @@ static int get_encode_fn(EncodeTiledFn *fn)
     return VELO_OK;
 }
 
-// rows x Gp fp16 row-major matrix, boxes of 128 rows x 64 genes (128 bytes), SWIZZLE_128B, zero fill outside
+// rows x Gp fp16 row-major matrix, boxes of 128 rows x kBK genes (one swizzle row), zero fill outside
 static int make_map(EncodeTiledFn enc, CUtensorMap *tm, const void *ptr, int64_t rows, int64_t Gp)
 {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Gp), static_cast<cuuint64_t>(rows)};
@@ -456,7 +732,7 @@ static int make_map(EncodeTiledFn enc, CUtensorMap *tm, const void *ptr, int64_t
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), 128u};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, kBK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VELO_REQUIRE(rc == CUDA_SUCCESS, "coldeltacor_tc: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(rc));
     return VELO_OK;
@@ -482,9 +758,13 @@ struct Scratch {
 
 using namespace velo;
 
+static std::atomic<int> g_tensor_cores{1};
+extern "C" void velo_set_tensor_cores(int enable) { g_tensor_cores.store(enable ? 1 : 0); }
+extern "C" int velo_get_tensor_cores(void) { return g_tensor_cores.load(); }
+
 extern "C" size_t velo_coldeltacor_tc_workspace_bytes(int64_t G, int64_t C, int64_t nc)
 {
-    const int64_t Gp = round_up(G, tc::kBK);
+    const int64_t Gp = round_up(G, tc::kGroup);
     return static_cast<size_t>(2 * (C + nc) * Gp * 2 + (C + nc) * 12 + G * 4 + 64 * G * 8 + 4096);
 }
 
@@ -503,7 +783,7 @@ extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int
     int rc = get_device_props(&dp);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
-    const int64_t Gp = round_up(G, kBK);
+    const int64_t Gp = round_up(G, kGroup);
     const int parts = 64;
 
     Scratch xh, xl, bh, bl, qd, pcc, mu, partial, isx, isb;
@@ -555,15 +835,36 @@ extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int
     p.c0 = c0;
     p.nc = nc;
     p.nkb = static_cast<int>(Gp / kBK);
+    p.drain_groups = 1;
+    if (const char *env = getenv("VELO_TC_DRAIN_GROUPS")) {   // experiment knob (profiles/r1_k2g_*): bias of long TMEM sums
+        const int v = atoi(env);
+        if (v >= 1 && v <= 4096) p.drain_groups = v;
+    }
     p.nI = static_cast<int>((nc + kTM - 1) / kTM);
-    p.nJ = static_cast<int>((C + kTN - 1) / kTN);
-    const int64_t tiles = static_cast<int64_t>(p.nI) * p.nJ;
-    VELO_REQUIRE(tiles < (1LL << 31), "coldeltacor_tc: too many tiles for one launch");
-    VELO_REQUIRE(static_cast<size_t>(dp.smem_optin) >= kSmemBytes, "coldeltacor_tc: needs %zu bytes of shared memory",
-                 kSmemBytes);
-    VELO_CUDA_TRY(cudaFuncSetAttribute(k_coldeltacor_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kSmemBytes)));
-    k_coldeltacor_tc<<<static_cast<unsigned>(tiles), kThreads, kSmemBytes, st>>>(tmXh, tmXl, tmBh, tmBl, p);
+    // variant: 2 = CTA pairs (cta_group::2, 128 x 256 pair tiles; default), 1 = single CTAs (128 x 128 tiles)
+    int variant = 2;
+    if (const char *env = getenv("VELO_TC_VARIANT")) variant = atoi(env) == 1 ? 1 : 2;
+    if (kBK != 64) variant = 1;                   // the SWIZZLE_64B experiment build only has the one-CTA kernel
+    if (variant == 1) {
+        p.nJ = static_cast<int>((C + kTN - 1) / kTN);
+        const int64_t tiles = static_cast<int64_t>(p.nI) * p.nJ;
+        VELO_REQUIRE(tiles < (1LL << 31), "coldeltacor_tc: too many tiles for one launch");
+        VELO_REQUIRE(static_cast<size_t>(dp.smem_optin) >= kSmemBytes, "coldeltacor_tc: needs %zu bytes of shared memory",
+                     kSmemBytes);
+        VELO_CUDA_TRY(cudaFuncSetAttribute(k_coldeltacor_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kSmemBytes)));
+        k_coldeltacor_tc<<<static_cast<unsigned>(tiles), kThreads, kSmemBytes, st>>>(tmXh, tmXl, tmBh, tmBl, p);
+    } else {
+        p.nJ = static_cast<int>((C + tc2::kTN - 1) / tc2::kTN);
+        const int64_t pairs = static_cast<int64_t>(p.nI) * p.nJ;
+        VELO_REQUIRE(2 * pairs < (1LL << 31), "coldeltacor_tc: too many tiles for one launch");
+        VELO_REQUIRE(static_cast<size_t>(dp.smem_optin) >= tc2::kSmemBytes,
+                     "coldeltacor_tc: needs %zu bytes of shared memory", tc2::kSmemBytes);
+        VELO_CUDA_TRY(cudaFuncSetAttribute(tc2::k_coldeltacor_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(tc2::kSmemBytes)));
+        tc2::k_coldeltacor_tc2<<<static_cast<unsigned>(2 * pairs), kThreads, tc2::kSmemBytes, st>>>(tmXh, tmXl, tmBh,
+                                                                                                   tmBl, p);
+    }
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }
