@@ -403,3 +403,25 @@ def test_tensor_core_linear_transition_probabilities(oracle):
     corr = dev.coldeltacor_linear_tc(dev.CellMajor.from_gene_major(e), dev.CellMajor.from_gene_major(d))
     tp = dev.transition_prob(corr, None, 0.05).cpu().numpy()
     np.testing.assert_allclose(tp, tp_want, rtol=1e-5, atol=0)
+
+
+def test_host_tier_pipelined_chunks_match_single_pass(oracle, monkeypatch):
+    """The host tier moves d / ixs / out in cell chunks underneath the kernel of the previous chunk (capi.cu);
+    forcing 7 ragged chunks on a small problem must reproduce the one-chunk result bit for bit, and a bad index
+    in a LATER chunk must still be rejected before its kernel runs."""
+    import velocyto_b200.estimation as est
+    from velocyto_b200 import _cabi
+    G, C, m = 900, 500, 40
+    e, d = synth(G, C, 31, "sqrt", 1.0)
+    ixs = rand_ixs(C, m, 32)
+    monkeypatch.delenv("VELO_HOST_CHUNK_CELLS", raising=False)
+    one = est.colDeltaCorSqrtpartial(e, d, ixs, psc=1.0, compact=True)
+    monkeypatch.setenv("VELO_HOST_CHUNK_CELLS", "77")
+    many = est.colDeltaCorSqrtpartial(e, d, ixs, psc=1.0, compact=True)
+    assert np.array_equal(one, many, equal_nan=True)
+    want = oracle.coldeltacor(e, d, ixs, "sqrt", 1.0)[np.arange(C)[:, None], ixs]
+    np.testing.assert_allclose(many, want, rtol=0, atol=5e-7)
+    bad = ixs.copy()
+    bad[C - 3, 5] = C + 7
+    with pytest.raises((_cabi.VeloError, ValueError)):
+        est.colDeltaCorSqrtpartial(e, d, bad, psc=1.0, compact=True)

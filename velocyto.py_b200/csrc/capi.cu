@@ -8,8 +8,10 @@
 // and bring the result back.  No host arithmetic on the data path.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
+#include <vector>
 
 #include "velo_common.cuh"
 
@@ -114,6 +116,156 @@ static int upload_cellmajor(const void *host_gc, int elem_bytes, int64_t G, int6
     return VELO_OK;
 }
 
+// Compact-output partial path, pipelined: the whole expression matrix e has to be resident before the first cell can be
+// processed (neighbours are arbitrary cells), but a cell's velocity row d_c, its neighbour list and its output row are
+// only needed while that cell is being processed.  So e goes up first, and d / ixs / out move in cell chunks on their own
+// streams underneath the correlation kernel of the previous chunk (at 100k x 30k: 24 GB of the 50 GB of H2D traffic and
+// all of the D2H traffic leave the critical path).
+static int host_partial_compact_pipelined(int transform, int rule, const void *e, const void *d, int elem_bytes,
+                                          const int64_t *ixs, int64_t G, int64_t C, int64_t m, double psc,
+                                          float *out_compact, double sigma, const DeviceProps &dp)
+{
+    const int64_t ld = round_up(G, 32);
+    const int64_t eb = elem_bytes;
+    // chunking: a multiple of the SM count (K1 strides cells statically over one persistent CTA per SM)
+    int64_t nchunks = (C * G * eb >= (2LL << 30)) ? 8 : 1;
+    int64_t chunk = round_up((C + nchunks - 1) / nchunks, dp.sm_count > 0 ? dp.sm_count : 148);
+    if (const char *env = getenv("VELO_HOST_CHUNK_CELLS")) {      // test hook: force the multi-chunk pipeline on small inputs
+        const long long v = atoll(env);
+        if (v > 0) chunk = v;
+    }
+    if (chunk > C) chunk = C;
+    nchunks = (C + chunk - 1) / chunk;
+
+    struct Streams {                 // declared FIRST: destroyed after every buffer has been handed back (cudaFreeAsync)
+        cudaStream_t st = nullptr, cp = nullptr, dd = nullptr;
+        std::vector<cudaEvent_t> ev;
+        void sync()
+        {
+            if (st) cudaStreamSynchronize(st);
+            if (cp) cudaStreamSynchronize(cp);
+            if (dd) cudaStreamSynchronize(dd);
+        }
+        ~Streams()
+        {
+            sync();
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            if (st) cudaStreamDestroy(st);
+            if (cp) cudaStreamDestroy(cp);
+            if (dd) cudaStreamDestroy(dd);
+        }
+    };
+    struct PinnedInts {
+        int *p = nullptr;
+        ~PinnedInts()
+        {
+            if (p) cudaFreeHost(p);
+        }
+    };
+    struct Quiesce {                 // declared LAST: on every exit path nothing is still using the buffers when they go
+        Streams &s;
+        ~Quiesce() { s.sync(); }
+    };
+    Streams S;
+    DevBuf e_cm, d_cm, stats, out, ix32, e_lo, lo_flag, stage_d, stage_ix, flags;
+    PinnedInts bad;
+    Quiesce quiesce{S};
+    VELO_CUDA_TRY(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    VELO_CUDA_TRY(cudaStreamCreateWithFlags(&S.cp, cudaStreamNonBlocking));
+    VELO_CUDA_TRY(cudaStreamCreateWithFlags(&S.dd, cudaStreamNonBlocking));
+    cudaStream_t st = S.st, cp = S.cp, dd = S.dd;
+    auto new_event = [&](cudaEvent_t *ev) -> int {
+        VELO_CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        S.ev.push_back(*ev);
+        return VELO_OK;
+    };
+    int rc;
+    if ((rc = e_cm.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
+    if ((rc = d_cm.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
+    if ((rc = stats.alloc(static_cast<size_t>(C) * 2 * 4, st))) return rc;
+    if ((rc = out.alloc(static_cast<size_t>(C * m) * 4, st))) return rc;
+    if ((rc = ix32.alloc(static_cast<size_t>(C * m) * 4, st))) return rc;
+    if ((rc = stage_d.alloc(static_cast<size_t>(chunk * G * eb), st))) return rc;
+    if ((rc = stage_ix.alloc(static_cast<size_t>(chunk * m) * 8, st))) return rc;
+    if ((rc = flags.alloc(static_cast<size_t>(nchunks) * sizeof(int), st))) return rc;
+    VELO_CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&bad.p), static_cast<size_t>(nchunks) * sizeof(int)));
+    VELO_CUDA_TRY(cudaMemsetAsync(flags.p, 0, static_cast<size_t>(nchunks) * sizeof(int), st));
+    if (ld != G) {
+        VELO_CUDA_TRY(cudaMemsetAsync(e_cm.p, 0, static_cast<size_t>(C * ld) * 4, st));
+        VELO_CUDA_TRY(cudaMemsetAsync(d_cm.p, 0, static_cast<size_t>(C * ld) * 4, st));
+    }
+    // fp64 inputs + a transform that jumps at zero difference: keep the fp32 residuals of e
+    const double jump = transform == VELO_SQRT ? 2.0 * sqrt(psc > 0 ? psc : 0.0)
+                        : transform == VELO_LOG10 ? 2.0 * fabs(log10(psc > 0 ? psc : 1e-300)) : 0.0;
+    const bool want_lo = elem_bytes == 8 && jump > 1e-4;
+    int lo_nonzero = 0;
+    if (want_lo) {
+        if ((rc = e_lo.alloc(static_cast<size_t>(C * ld) * 4, st))) return rc;
+        if ((rc = lo_flag.alloc(sizeof(int), st))) return rc;
+        VELO_CUDA_TRY(cudaMemsetAsync(e_lo.p, 0, static_cast<size_t>(C * ld) * 4, st));
+        VELO_CUDA_TRY(cudaMemsetAsync(lo_flag.p, 0, sizeof(int), st));
+    }
+    cudaEvent_t ev_alloc;
+    if ((rc = new_event(&ev_alloc))) return rc;
+    VELO_CUDA_TRY(cudaEventRecord(ev_alloc, st));
+    VELO_CUDA_TRY(cudaStreamWaitEvent(cp, ev_alloc, 0));          // the copy stream may touch the buffers from here on
+
+    // e: all of it, on the copy stream (the first d chunk queues up right behind it)
+    if ((rc = upload_cellmajor(e, elem_bytes, G, C, e_cm.as<float>(), ld, cp, want_lo ? e_lo.as<float>() : nullptr,
+                               want_lo ? lo_flag.as<int>() : nullptr)))
+        return rc;
+    cudaEvent_t ev_e;
+    if ((rc = new_event(&ev_e))) return rc;
+    if (want_lo) VELO_CUDA_TRY(cudaMemcpyAsync(&lo_nonzero, lo_flag.p, sizeof(int), cudaMemcpyDeviceToHost, cp));
+    VELO_CUDA_TRY(cudaEventRecord(ev_e, cp));
+
+    std::vector<cudaEvent_t> ev_ready(nchunks), ev_out(nchunks);
+    auto enqueue_copy = [&](int64_t j) -> int {                   // H2D + layout conversion of chunk j, copy stream
+        const int64_t c0 = j * chunk, nc = (C - c0 < chunk) ? C - c0 : chunk;
+        VELO_CUDA_TRY(cudaMemcpy2DAsync(stage_d.p, static_cast<size_t>(nc * eb), static_cast<const char *>(d) + c0 * eb,
+                                        static_cast<size_t>(C * eb), static_cast<size_t>(nc * eb), static_cast<size_t>(G),
+                                        cudaMemcpyHostToDevice, cp));
+        int r = velo_dev_pack_cellmajor(stage_d.p, elem_bytes, G, nc, d_cm.as<float>() + c0 * ld, ld, 0, cp);
+        if (r) return r;
+        VELO_CUDA_TRY(cudaMemcpyAsync(stage_ix.p, ixs + c0 * m, static_cast<size_t>(nc * m) * 8, cudaMemcpyHostToDevice, cp));
+        if ((r = i64_to_i32_checked(stage_ix.as<int64_t>(), ix32.as<int32_t>() + c0 * m, nc * m, C, flags.as<int>() + j, cp)))
+            return r;
+        VELO_CUDA_TRY(cudaMemcpyAsync(bad.p + j, flags.as<int>() + j, sizeof(int), cudaMemcpyDeviceToHost, cp));
+        if ((r = new_event(&ev_ready[j]))) return r;
+        VELO_CUDA_TRY(cudaEventRecord(ev_ready[j], cp));
+        return VELO_OK;
+    };
+    if ((rc = enqueue_copy(0))) return rc;
+    VELO_CUDA_TRY(cudaEventSynchronize(ev_e));                    // lo_nonzero is known; e is resident
+    VELO_CUDA_TRY(cudaStreamWaitEvent(st, ev_e, 0));
+    for (int64_t j = 0; j < nchunks; ++j) {
+        const int64_t c0 = j * chunk, nc = (C - c0 < chunk) ? C - c0 : chunk;
+        if (j + 1 < nchunks && (rc = enqueue_copy(j + 1))) return rc;      // flies under this chunk's kernel
+        VELO_CUDA_TRY(cudaEventSynchronize(ev_ready[j]));
+        // the kernel must not gather through an out-of-range index: check before launching it
+        VELO_REQUIRE(bad.p[j] == 0, "colDeltaCor: ixs holds an index outside [0, %lld)", static_cast<long long>(C));
+        VELO_CUDA_TRY(cudaStreamWaitEvent(st, ev_ready[j], 0));
+        if ((rc = velo_dev_cell_stats(d_cm.as<float>() + c0 * ld, ld, G, nc, stats.as<float>() + 2 * c0, st))) return rc;
+        if ((rc = velo_dev_coldeltacor_ex(transform, rule, e_cm.as<float>(), lo_nonzero ? e_lo.as<float>() : nullptr,
+                                          d_cm.as<float>() + c0 * ld, ld, stats.as<float>() + 2 * c0,
+                                          ix32.as<int32_t>() + c0 * m, m, out.as<float>() + c0 * m, m, G, C, c0, nc, m, psc,
+                                          st)))
+            return rc;
+        if (sigma > 0.0 && (rc = velo_dev_transition_prob(out.as<float>() + c0 * m, m, ix32.as<int32_t>() + c0 * m, m,
+                                                          out.as<float>() + c0 * m, m, c0, nc, m, sigma, st)))
+            return rc;
+        if ((rc = new_event(&ev_out[j]))) return rc;
+        VELO_CUDA_TRY(cudaEventRecord(ev_out[j], st));
+        VELO_CUDA_TRY(cudaStreamWaitEvent(dd, ev_out[j], 0));
+        VELO_CUDA_TRY(cudaMemcpyAsync(out_compact + c0 * m, out.as<float>() + c0 * m, static_cast<size_t>(nc * m) * 4,
+                                      cudaMemcpyDeviceToHost, dd));
+    }
+    VELO_CUDA_TRY(cudaStreamSynchronize(st));
+    VELO_CUDA_TRY(cudaStreamSynchronize(dd));
+    VELO_CUDA_TRY(cudaStreamSynchronize(cp));
+    return VELO_OK;
+}
+
 // Shared body of the host tier.  Exactly one of (rm, out_compact) is non-null.
 static int host_coldeltacor(int transform, int rule, const void *e, const void *d, int elem_bytes,
                             const int64_t *ixs, int64_t rows, int64_t cols, int64_t nrndm, double psc, double *rm,
@@ -129,6 +281,8 @@ static int host_coldeltacor(int transform, int rule, const void *e, const void *
     const int64_t G = rows, C = cols;
     const int64_t m = ixs ? nrndm : C;
     if (m == 0) return VELO_OK;
+    if (out_compact && ixs)
+        return host_partial_compact_pipelined(transform, rule, e, d, elem_bytes, ixs, G, C, m, psc, out_compact, sigma, dp);
     const int64_t ld = round_up(G, 32);
 
     cudaStream_t st;

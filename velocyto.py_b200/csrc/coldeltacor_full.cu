@@ -55,11 +55,14 @@ __global__ void __launch_bounds__(kFullThreads, 2) k_coldeltacor_full(const Full
     const float *ei_ptr = p.e_cm + (targ_ok ? targ_i : 0) * p.ld;
     const float mu = cell_ok ? p.stats[2 * cell_r] : 0.f;
 
-    float s1[4][4], s2[4][4], s3[4][4];
+    // sums over -A (s1), A^2 (s2) and A*b (s3) for 4 cells x 4 targets, held as fp32x2 pairs of adjacent targets:
+    // the three updates per pair are packed FADD2/FFMA2 (two fp32 operations per issue slot), which leaves the
+    // MUFU unit (one sqrt/lg2 per pair, 16 lanes per SM) as the only limiter instead of instruction issue
+    float2 s1[4][2], s2[4][2], s3[4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s1[a][b] = s2[a][b] = s3[a][b] = 0.f;
+        for (int h = 0; h < 2; ++h) s1[a][h] = s2[a][h] = s3[a][h] = make_float2(0.f, 0.f);
 
     float4 rc[2], rd[2], ri[2];
     auto gload = [&](int64_t k0) {
@@ -102,16 +105,21 @@ __global__ void __launch_bounds__(kFullThreads, 2) k_coldeltacor_full(const Full
             const float4 b4 = *reinterpret_cast<const float4 *>(tb + g * 64);
             const float4 i4 = *reinterpret_cast<const float4 *>(ti + g * 64);
             const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-            const float iv[4] = {i4.x, i4.y, i4.z, i4.w};
+            const float2 iv[2] = {make_float2(i4.x, i4.y), make_float2(i4.z, i4.w)};
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a) {
+                const float2 ca = make_float2(cv[a], cv[a]);
+                const float2 nb = make_float2(-bv[a], -bv[a]);
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const float nA = full_transform_neg<TR>(cv[a] - iv[b], p.psc);   // = -A
-                    s1[a][b] -= nA;
-                    s2[a][b] = fmaf(nA, nA, s2[a][b]);
-                    s3[a][b] = fmaf(-nA, bv[a], s3[a][b]);
+                for (int h = 0; h < 2; ++h) {
+                    const float2 u = sub2(ca, iv[h]);                                      // e_c - e_i
+                    const float2 nA = make_float2(full_transform_neg<TR>(u.x, p.psc),      // = -A
+                                                  full_transform_neg<TR>(u.y, p.psc));
+                    s1[a][h] = add2(s1[a][h], nA);
+                    s2[a][h] = fma2(nA, nA, s2[a][h]);
+                    s3[a][h] = fma2(nA, nb, s3[a][h]);                                     // (-A) * (-b)
                 }
+            }
         }
         if (ch + 1 < nchunks) {
             sstore(stage ^ 1);                                  // other buffer: last read two iterations ago
@@ -129,7 +137,9 @@ __global__ void __launch_bounds__(kFullThreads, 2) k_coldeltacor_full(const Full
         for (int b = 0; b < 4; ++b) {
             const int64_t i = i_base + 4 * tx + b;
             if (i >= p.C) continue;
-            const double S1 = s1[a][b], S2 = s2[a][b], S3 = s3[a][b];
+            const float2 p1 = s1[a][b >> 1], p2 = s2[a][b >> 1], p3 = s3[a][b >> 1];
+            const double S1 = -static_cast<double>((b & 1) ? p1.y : p1.x), S2 = (b & 1) ? p2.y : p2.x,
+                         S3 = (b & 1) ? p3.y : p3.x;
             const double var = S2 - S1 * S1 * invG;
             const double corr = (var > 0.0 && ssb > 0.0) ? S3 / sqrt(var * ssb) : __longlong_as_double(0x7ff8000000000000LL);
             p.out[r * p.out_ld + i] = static_cast<float>(corr);

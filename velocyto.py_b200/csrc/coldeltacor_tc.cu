@@ -659,37 +659,64 @@ k_tc_prep(const float *e_cm, const float *d_cm, int64_t ld, const float *mu, con
     const bool local = r >= 0 && r < nc;
     const float *drow = local ? d_cm + r * ld : nullptr;
     const float dm = local ? stats[2 * r] : 0.f;
+    // quads of genes: rows are 16-byte aligned, ld % 4 == 0, mu holds Gp zero-padded entries
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     double s = 0.0;
     float mx = 0.f, mb = 0.f;
-    for (int64_t g = threadIdx.x; g < G; g += blockDim.x) {
-        const float v = erow[g] - mu[g];
-        s += static_cast<double>(v);
-        mx = fmaxf(mx, fabsf(v));
-        if (local) mb = fmaxf(mb, fabsf(drow[g] - dm));
+    for (int64_t g = 4 * static_cast<int64_t>(threadIdx.x); g < G; g += 4 * blockDim.x) {
+        const float4 ev = *reinterpret_cast<const float4 *>(erow + g);
+        const float4 mv = *reinterpret_cast<const float4 *>(mu + g);
+        const float4 dv = local ? *reinterpret_cast<const float4 *>(drow + g) : z4;
+        const float v[4] = {ev.x - mv.x, ev.y - mv.y, ev.z - mv.z, ev.w - mv.w};
+        const float w[4] = {dv.x - dm, dv.y - dm, dv.z - dm, dv.w - dm};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (g + i < G) {
+                s += static_cast<double>(v[i]);
+                mx = fmaxf(mx, fabsf(v[i]));
+                if (local) mb = fmaxf(mb, fabsf(w[i]));
+            }
     }
     const float rm = static_cast<float>(block_sum(s, sh) / static_cast<double>(G));
     const float sx = pow2_scale(block_max(mx, shf) + fabsf(rm));      // |x| <= max |e - mu| + |row mean|
     const float sb = pow2_scale(block_max(mb, shf));
     double q = 0.0, pc = 0.0;
-    for (int64_t g = threadIdx.x; g < Gp; g += blockDim.x) {
-        float x = 0.f, b = 0.f;
+    for (int64_t g = 4 * static_cast<int64_t>(threadIdx.x); g < Gp; g += 4 * blockDim.x) {
+        float x[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
         if (g < G) {
-            x = (erow[g] - mu[g]) - rm;
-            if (local) b = drow[g] - dm;
+            const float4 ev = *reinterpret_cast<const float4 *>(erow + g);
+            const float4 mv = *reinterpret_cast<const float4 *>(mu + g);
+            const float4 dv = local ? *reinterpret_cast<const float4 *>(drow + g) : z4;
+            const float xe[4] = {ev.x - mv.x, ev.y - mv.y, ev.z - mv.z, ev.w - mv.w};
+            const float be[4] = {dv.x - dm, dv.y - dm, dv.z - dm, dv.w - dm};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (g + i < G) {
+                    x[i] = xe[i] - rm;
+                    if (local) b[i] = be[i];
+                }
         }
-        const float xs = x * sx;
-        const __half xh = __float2half_rn(xs);
-        const __half xl = __float2half_rn(xs - __half2float(xh));
-        Xh[c * Gp + g] = xh;
-        Xl[c * Gp + g] = xl;
-        q += static_cast<double>(x) * static_cast<double>(x);
+        __align__(8) __half xh[4], xl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float xs = x[i] * sx;
+            xh[i] = __float2half_rn(xs);
+            xl[i] = __float2half_rn(xs - __half2float(xh[i]));
+            q += static_cast<double>(x[i]) * static_cast<double>(x[i]);
+        }
+        *reinterpret_cast<uint2 *>(Xh + c * Gp + g) = *reinterpret_cast<const uint2 *>(xh);
+        *reinterpret_cast<uint2 *>(Xl + c * Gp + g) = *reinterpret_cast<const uint2 *>(xl);
         if (local) {
-            const float bs = b * sb;
-            const __half bh = __float2half_rn(bs);
-            const __half bl = __float2half_rn(bs - __half2float(bh));
-            Bh[r * Gp + g] = bh;
-            Bl[r * Gp + g] = bl;
-            pc += static_cast<double>(x) * static_cast<double>(b);
+            __align__(8) __half bh[4], bl[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float bs = b[i] * sb;
+                bh[i] = __float2half_rn(bs);
+                bl[i] = __float2half_rn(bs - __half2float(bh[i]));
+                pc += static_cast<double>(x[i]) * static_cast<double>(b[i]);
+            }
+            *reinterpret_cast<uint2 *>(Bh + r * Gp + g) = *reinterpret_cast<const uint2 *>(bh);
+            *reinterpret_cast<uint2 *>(Bl + r * Gp + g) = *reinterpret_cast<const uint2 *>(bl);
         }
     }
     q = block_sum(q, sh);
@@ -776,6 +803,8 @@ extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int
     VELO_REQUIRE(e_cm && d_cm && stats && out, "coldeltacor_tc: null pointer");
     VELO_REQUIRE(G > 0 && C > 0 && nc >= 0 && c0 >= 0 && c0 + nc <= C, "coldeltacor_tc: bad sizes");
     VELO_REQUIRE(ld >= G && out_ld >= C, "coldeltacor_tc: leading dimensions too small");
+    VELO_REQUIRE((ld % 4) == 0 && (reinterpret_cast<uintptr_t>(e_cm) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_cm) & 15) == 0,
+                 "coldeltacor_tc: e_cm/d_cm must be 16-byte aligned with ld a multiple of 4");
     VELO_REQUIRE(C < (1LL << 31) - 256 && G < (1LL << 31) - 64, "coldeltacor_tc: sizes must fit int32 TMA coordinates");
     VELO_REQUIRE((dbgP == nullptr) == (dbgQ == nullptr), "coldeltacor_tc: dbgP and dbgQ go together");
     if (nc == 0) return VELO_OK;
@@ -793,7 +822,8 @@ extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int
     if ((rc = bl.alloc(static_cast<size_t>(nc * Gp) * 2, st))) return rc;
     if ((rc = qd.alloc(static_cast<size_t>(C) * 8, st))) return rc;
     if ((rc = pcc.alloc(static_cast<size_t>(nc) * 8, st))) return rc;
-    if ((rc = mu.alloc(static_cast<size_t>(G) * 4, st))) return rc;
+    if ((rc = mu.alloc(static_cast<size_t>(Gp) * 4, st))) return rc;
+    VELO_CUDA_TRY(cudaMemsetAsync(mu.p, 0, static_cast<size_t>(Gp) * 4, st));
     if ((rc = isx.alloc(static_cast<size_t>(C) * 4, st))) return rc;
     if ((rc = isb.alloc(static_cast<size_t>(nc) * 4, st))) return rc;
     if ((rc = partial.alloc(static_cast<size_t>(parts) * G * 8, st))) return rc;
