@@ -205,6 +205,12 @@ int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_cm, const f
                          const float *Ux_cm, int64_t ld, int64_t G, int64_t C, double perc_lo,
                          double perc_hi, float *W_cm, int64_t ldw, velo_stream_t stream);
 
+/* As velo_dev_fit_weights plus kind 5 "maxmin_weighted" (analysis.py:1186-1192): W = (R^power + (1-R)^power) / 2 with
+ * R = S clipped to its [perc_lo, perc_hi] percentiles and rescaled to [0, 1] (power = maxmin_weighted_pow). */
+int velo_dev_fit_weights_ex(int kind, const float *S_cm, const float *U_cm, const float *Sx_cm,
+                            const float *Ux_cm, int64_t ld, int64_t G, int64_t C, double perc_lo,
+                            double perc_hi, double power, float *W_cm, int64_t ldw, velo_stream_t stream);
+
 /* As velo_dev_fit_gammas with the non-default options: hi_per_gene (G fp64, device; limit_gamma's per-gene upper
  * slope bound, estimation.py:199-204/229-234) and q_fixed (G fp64, device; fixperc_q's pinned offset,
  * estimation.py:221-224/254-257); either may be NULL.  velo_dev_fit_constraints computes both from the data. */
@@ -254,6 +260,15 @@ int velo_dev_patch_corr(float *corr, int64_t ld, const int32_t *ixs, int64_t ixs
 int velo_dev_embedding_shift(const float *P, int64_t ld, const int32_t *ixs, int64_t ixs_ld,
                              const double *embedding, int dims, int64_t c0, int64_t nc, int64_t m,
                              double *out, velo_stream_t stream);
+
+/* ---- size / log normalisation (the `normalize` family, analysis.py:535-676) ----
+ * sums[c] = sum_g X[c, g] (= X.sum(0) of the reference's gene-major matrix), fp64 (device, C values) */
+int velo_dev_cell_sums(const float *X_cm, int64_t ld, int64_t G, int64_t C, double *sums, velo_stream_t stream);
+/* out_sz = factor[c] * X (factor: C fp64 on the device, NULL = 1; non-finite -> 0 when nonfinite_to_zero != 0, the guard
+ * of _normalize_U/_normalize_Ux analysis.py:581,630); out_norm = log2(out_sz + pcount).  Either output may be NULL. */
+int velo_dev_size_normalize(const float *X_cm, int64_t ld, int64_t G, int64_t C, const double *factor,
+                            double pcount, int nonfinite_to_zero, float *out_sz, float *out_norm,
+                            velo_stream_t stream);
 
 /* ---- kNN smoothing (K5): out[c,:] = sum_p weights[p] * S[indices[p],:], p in [indptr[c], indptr[c+1])
  * = convolve_by_sparse_weights(data, w) with w in CSR by rows (neighbors.py:416-423, weights from

@@ -252,8 +252,54 @@ def golden_pipeline(an, out):
     np.savez_compressed(os.path.join(out, "pipeline_small.npz"), **res)
 
 
+def golden_normalize(an, out):
+    """The size/log normalisation family (analysis.py:535-676) on hand-built objects."""
+    if an is None:
+        print("skipping normalize golden (analysis.py not importable)")
+        return
+    G, C = 40, 31
+    S, U = synth_counts(G, C, 21)
+    U[:, 4] = 0.0                                   # a cell without unspliced molecules: 0/0 -> guard (analysis.py:581)
+    rng = np.random.default_rng(22)
+    Sx = S + rng.uniform(0, 1, S.shape)
+    Ux = U + rng.uniform(0, 1, U.shape)
+
+    def fresh():
+        vlm = an.VelocytoLoom.__new__(an.VelocytoLoom)
+        vlm.S, vlm.U, vlm.A = S.copy(), U.copy(), np.zeros_like(S)
+        vlm.Sx, vlm.Ux = Sx.copy(), Ux.copy()
+        vlm.ca, vlm.ra = {"CellID": np.arange(C)}, {"Gene": np.arange(G)}
+        return vlm
+
+    res = {"S": S, "U": U, "Sx": Sx, "Ux": Ux}
+    cases = {"default": dict(which="both"),
+             "opts": dict(which="both", pcount=0.5, use_S_size_for_U=True, target_size=(1000.0, 500.0)),
+             "nosize": dict(which="both", size=False),
+             "nolog": dict(which="both", log=False),
+             "relsize": dict(which="both", relative_size=np.linspace(50.0, 400.0, C)),
+             "imputed": dict(which="imputed"),
+             "imputed_opts": dict(which="imputed", pcount=2.0, use_S_size_for_U=True, target_size=(800.0, None))}
+    import warnings
+    for tag, kw in cases.items():
+        vlm = fresh()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with np.errstate(all="ignore"):
+                vlm.normalize(**kw)
+        for name in ("S_sz", "S_norm", "U_sz", "U_norm", "Sx_sz", "Sx_norm", "Ux_sz", "Ux_norm", "cell_size", "avg_size",
+                     "norm_factor", "Ucell_size", "Uavg_size", "Unorm_factor", "xcell_size", "xavg_size", "xnorm_factor",
+                     "xUcell_size", "xUavg_size", "xUnorm_factor"):
+            if hasattr(vlm, name):
+                res[f"{tag}__{name}"] = np.asarray(getattr(vlm, name), dtype=np.float64)
+    np.savez_compressed(os.path.join(out, "normalize_small.npz"), **res)
+
+
 def main():
     sb, est, nb, an = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "normalize":     # add one fixture without touching the others
+        golden_normalize(an, HERE)
+        return
+    golden_normalize(an, HERE)
     golden_coldeltacor(est, HERE)
     golden_fits(est, an, HERE)
     golden_smoothing(nb, HERE)

@@ -171,3 +171,35 @@ def test_sampler_matches_golden(oracle, golden):
     neigh, samp = oracle.sample_neighbors(knn_idx, 0.5, (0.5, 0.1), 15071990)
     assert np.array_equal(samp, g["sampling_ixs"])
     assert np.array_equal(neigh, g["neigh_ixs"])
+
+
+def test_normalize_oracle_matches_golden(oracle, golden):
+    """analysis.py:535-676 restated in oracle.size_log_normalize == the reference's normalize() outputs."""
+    g = golden("normalize_small.npz")
+    S, U, Sx, Ux = g["S"], g["U"], g["Sx"], g["Ux"]
+    C = S.shape[1]
+
+    def check(tag, name_sz, name_norm, got):
+        X_sz, X_norm = got[0], got[1]
+        np.testing.assert_allclose(X_sz, g[f"{tag}__{name_sz}"], rtol=1e-14, atol=0, equal_nan=True)
+        if f"{tag}__{name_norm}" in g.files:
+            np.testing.assert_allclose(X_norm, g[f"{tag}__{name_norm}"], rtol=1e-14, atol=1e-15, equal_nan=True)
+        else:
+            assert X_norm is None
+
+    r = oracle.size_log_normalize(S)
+    check("default", "S_sz", "S_norm", r)
+    np.testing.assert_array_equal(r[2], g["default__cell_size"])
+    check("default", "U_sz", "U_norm", oracle.size_log_normalize(U, guard=True))
+    check("opts", "S_sz", "S_norm", oracle.size_log_normalize(S, pcount=0.5, target_size=1000.0))
+    check("opts", "U_sz", "U_norm", oracle.size_log_normalize(U, pcount=0.5, cell_size=S.sum(0), target_size=500.0, guard=True))
+    check("nosize", "S_sz", "S_norm", oracle.size_log_normalize(S, size=False))
+    check("nolog", "U_sz", "U_norm", oracle.size_log_normalize(U, log=False, guard=True))
+    rel = np.linspace(50.0, 400.0, C)
+    check("relsize", "S_sz", "S_norm", oracle.size_log_normalize(S, cell_size=rel))
+    check("relsize", "U_sz", "U_norm", oracle.size_log_normalize(U, cell_size=rel, guard=True))
+    check("imputed", "Sx_sz", "Sx_norm", oracle.size_log_normalize(Sx))
+    check("imputed", "Ux_sz", "Ux_norm", oracle.size_log_normalize(Ux, guard=True))
+    check("imputed_opts", "Sx_sz", "Sx_norm", oracle.size_log_normalize(Sx, pcount=2.0, target_size=800.0))
+    # use_Sx_size without a previous S normalisation: hasattr(self, "cell_size") is False -> Sx.sum(0) (analysis.py:607-610)
+    check("imputed_opts", "Ux_sz", "Ux_norm", oracle.size_log_normalize(Ux, pcount=2.0, cell_size=Sx.sum(0), guard=True))

@@ -337,7 +337,7 @@ def test_row_percentiles_match_numpy():
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("kind", ["maxmin_diag", "maxmin", "maxmin_double", "sum", "prod"])
+@pytest.mark.parametrize("kind", ["maxmin_diag", "maxmin", "maxmin_double", "sum", "prod", "maxmin_weighted"])
 def test_fit_weights_match_oracle(oracle, kind):
     """Weights of fit_gammas built on the device == analysis.py:1181-1219 evaluated on the same fp32-rounded inputs."""
     from velocyto_b200 import device as dev
@@ -349,7 +349,7 @@ def test_fit_weights_match_oracle(oracle, kind):
     Sd, Ud = dev.CellMajor.from_gene_major(Sx), dev.CellMajor.from_gene_major(Ux)
     W = dev.fit_weights(kind, Sd, Ud, Sd, Ud, (2, 98)).to_gene_major()
     want = oracle.gamma_fit_weights(kind, Sx, Ux, Sx, Ux, (2, 98))
-    if kind in ("sum", "prod"):
+    if kind in ("sum", "prod", "maxmin_weighted"):
         np.testing.assert_allclose(W, want, rtol=2e-6, atol=1e-7)
     else:
         # binary weights: identical except (at most) cells sitting exactly on an interpolated threshold
@@ -464,3 +464,63 @@ def test_device_knn_graphs_match_reference_golden(golden):
         gph = b.kneighbors_graph(mode="distance")
         assert np.array_equal(gph.indices, s[f"bknn_{tag}_indices"])
         np.testing.assert_allclose(gph.data, s[f"bknn_{tag}_data"], rtol=1e-12, atol=1e-15)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# normalize family on the device (analysis.py:535-676)
+
+_NORM_CASES = {"default": dict(which="both"),
+               "opts": dict(which="both", pcount=0.5, use_S_size_for_U=True, target_size=(1000.0, 500.0)),
+               "nosize": dict(which="both", size=False),
+               "nolog": dict(which="both", log=False),
+               "relsize": "relsize",
+               "imputed": dict(which="imputed"),
+               "imputed_opts": dict(which="imputed", pcount=2.0, use_S_size_for_U=True, target_size=(800.0, None))}
+
+
+@pytest.mark.parametrize("tag", list(_NORM_CASES))
+def test_normalize_matches_reference_golden(golden, tag):
+    """VelocytoLoom.normalize on the device == the reference's outputs, attribute by attribute (fp32 storage: 2e-7)."""
+    from velocyto_b200.analysis import VelocytoLoom
+    g = golden("normalize_small.npz")
+    C = g["S"].shape[1]
+    kw = _NORM_CASES[tag]
+    if kw == "relsize":
+        kw = dict(which="both", relative_size=np.linspace(50.0, 400.0, C))
+    vlm = VelocytoLoom(S=g["S"].copy(), U=g["U"].copy())
+    vlm.Sx, vlm.Ux = g["Sx"].copy(), g["Ux"].copy()
+    vlm.normalize(**kw)
+    checked = 0
+    for key in g.files:
+        if not key.startswith(tag + "__"):
+            continue
+        name = key.split("__", 1)[1]
+        want = g[key]
+        got = np.asarray(getattr(vlm, name), dtype=np.float64)
+        assert got.shape == want.shape, name
+        np.testing.assert_allclose(got, want, rtol=2e-7, atol=1e-7, equal_nan=True, err_msg=name)
+        checked += 1
+    assert checked >= 3
+    for name in ("S_norm", "U_norm", "Sx_norm", "Ux_norm"):          # not created when the reference does not create it
+        if f"{tag}__{name}" not in g.files:
+            assert not hasattr(vlm, name)
+
+
+def test_normalize_medium_matches_oracle(oracle):
+    """3000 genes x 2000 cells incl. an empty cell (0/0 -> NaN in S, guarded to 0 in U) and ragged gene count."""
+    from velocyto_b200 import device as dev
+    G, C = 3001, 2000
+    S, U = synth_counts(G, C, 91)
+    S[:, 7] = 0.0
+    U[:, 7] = 0.0
+    Sd, Ud = dev.CellMajor.from_gene_major(S), dev.CellMajor.from_gene_major(U)
+    cs = dev.cell_sums(Sd).cpu().numpy()
+    np.testing.assert_array_equal(cs, S.sum(0))                     # integer counts: exact in fp64
+    import torch
+    for X, Xd, guard in ((S, Sd, False), (U, Ud, True)):
+        want_sz, want_nm, wcs, _, nf = oracle.size_log_normalize(X.copy(), pcount=1, guard=guard)
+        fac = torch.from_numpy(np.ascontiguousarray(nf)).cuda()
+        sz, nm = dev.size_normalize(Xd, fac, 1.0, nonfinite_to_zero=guard)
+        np.testing.assert_allclose(sz.to_gene_major(), want_sz, rtol=2e-7, atol=0, equal_nan=True)
+        np.testing.assert_allclose(nm.to_gene_major(), want_nm, rtol=2e-7, atol=2e-7, equal_nan=True)
+        assert float(sz.t[:, G:].abs().sum()) == 0.0 and float(nm.t[:, G:].abs().sum()) == 0.0   # pad columns stay zero

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "velo_dev_fit_constraints": (_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "velo_dev_row_percentiles": (_int, [_ptr, _i64, _i64, _ptr, _int, _ptr, _ptr]),
     "velo_dev_fit_weights": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl, _ptr, _i64, _ptr]),
+    "velo_dev_fit_weights_ex": (_int, [_int, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl, _dbl, _ptr, _i64, _ptr]),
     "velo_dev_velocity_chain": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _int, _dbl, _dbl, _int, _int,
                                        _dbl, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "velo_dev_velocity_threshold": (_int, [_ptr, _i64, _ptr, _ptr, _i64, _i64, _dbl, _ptr, _ptr]),
@@ -71,6 +72,8 @@ PROTOTYPES = {
     "velo_dev_row_cosine_scale": (_int, [_ptr, _ptr, _i64, _i64, _i64, _dbl, _ptr, _ptr]),
     "velo_dev_patch_corr": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _int, _ptr, _ptr]),
     "velo_dev_embedding_shift": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _int, _i64, _i64, _i64, _ptr, _ptr]),
+    "velo_dev_cell_sums": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
+    "velo_dev_size_normalize": (_int, [_ptr, _i64, _i64, _i64, _ptr, _dbl, _int, _ptr, _ptr, _ptr]),
     "velo_dev_knn_smooth": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "velo_dev_knn_smooth_csr": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _ptr]),
     "velo_dev_knn": (_int, [_ptr, _i64, _int, _int, _int, _ptr, _ptr, _ptr]),

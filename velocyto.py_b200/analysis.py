@@ -15,9 +15,10 @@ What stays on the host, as in the reference: the kNN searches (scikit-learn, ana
 SURVEY.md 8f "next"), the neighbour sampler and the randomised control (NumPy / numba RNG streams must
 match the reference's, analysis.py:1552-1566, 2407-2420), and the O(nnz) graph bookkeeping.
 
-Out of scope: loom I/O, filtering, normalisation, PCA/TSNE, plotting, Markov.
-Objects are therefore built from arrays: ``VelocytoLoom(S=..., U=...)``, then the caller sets
-``S_sz``/``U_sz``/``pcs``/``ts`` exactly as the reference's preprocessing methods would have.
+The size/log normalisation family (``normalize``, analysis.py:535-676) also runs on the device (SURVEY.md 8f "next").
+Out of scope: loom I/O, filtering, PCA/TSNE, plotting, Markov.
+Objects are therefore built from arrays: ``VelocytoLoom(S=..., U=...)``, then ``normalize(...)`` and the caller sets
+``pcs``/``ts`` exactly as the reference's ``perform_PCA`` / embedding methods would have.
 """
 from __future__ import annotations
 
@@ -33,7 +34,7 @@ from .neighbors import connectivity_to_weights
 
 # (genes, cells) matrices that live on the device once a hot method has produced or consumed them
 _MATRIX_ATTRS = ("S", "U", "S_sz", "U_sz", "Sx", "Ux", "Sx_sz", "Ux_sz", "Upred", "velocity", "delta_S",
-                 "Sx_sz_t", "Sx_t", "delta_S_rndm")
+                 "Sx_sz_t", "Sx_t", "delta_S_rndm", "S_norm", "U_norm", "Sx_norm", "Ux_norm")
 
 
 class _DeviceBacked:
@@ -150,6 +151,108 @@ class VelocytoLoom:
         self.__dict__.setdefault("_host", {}).pop(name, None)
         self.__dict__.setdefault("_fp32_exact", set()).discard(name)
 
+    # ------------------------------------------------------------------ normalize (analysis.py:535-676)
+    def _size_log_normalize(self, src: str, size: bool, log: bool, pcount: float, cell_size, target_size,
+                            guard: bool, dst_sz: str, dst_norm: str):
+        """Shared body of ``_normalize_S/_U/_Sx/_Ux``: per-cell totals (``velo_dev_cell_sums``) unless a size vector
+        is given, ``norm_factor = avg_size / cell_size`` in float64 on the host (C values), then one device pass writing
+        ``X_sz`` and, with ``log``, ``X_norm = log2(X_sz + pcount)``.  Returns ``(cell_size, avg_size, norm_factor)``."""
+        import torch
+        from . import device as dev
+        X = self._dev(src)
+        if size:
+            if cell_size is None:
+                cell_size = dev.cell_sums(X).cpu().numpy()
+            cell_size = np.asarray(cell_size)
+            avg_size = cell_size.mean() if target_size is None else target_size
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    norm_factor = avg_size / cell_size
+            fac = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(norm_factor, (X.C,)), dtype=np.float64)).to(X.t.device)
+        else:
+            avg_size, norm_factor, fac = None, 1, None
+        sz, nm = dev.size_normalize(X, fac, pcount, want_sz=True, want_norm=bool(log), nonfinite_to_zero=guard)
+        self._set_dev(dst_sz, sz)
+        if log:
+            self._set_dev(dst_norm, nm)
+        return cell_size, avg_size, norm_factor
+
+    def _normalize_S(self, size: bool = True, log: bool = True, pcount: float = 1, relative_size=None,
+                     target_size=None) -> None:
+        """analysis.py:535-552: creates ``cell_size``, ``avg_size``, ``norm_factor``, ``S_sz`` and ``S_norm``."""
+        cs, avg, nf = self._size_log_normalize("S", size, log, pcount,
+                                               relative_size if type(relative_size) is np.ndarray else None,
+                                               target_size, False, "S_sz", "S_norm")
+        if size:
+            self.cell_size, self.avg_size = cs, avg
+        self.norm_factor = nf
+
+    def _normalize_U(self, size: bool = True, log: bool = True, pcount: float = 1, use_S_size: bool = False,
+                     relative_size=None, target_size=None) -> None:
+        """analysis.py:554-584 (non-finite ``U_sz`` -> 0, :581)."""
+        given = None
+        if size:
+            if use_S_size:
+                given = self.cell_size if hasattr(self, "cell_size") else self._host_or_dev_sums("S")
+            elif type(relative_size) is np.ndarray:
+                given = relative_size
+        cs, avg, nf = self._size_log_normalize("U", size, log, pcount, given, target_size, True, "U_sz", "U_norm")
+        if size:
+            self.Ucell_size, self.Uavg_size = cs, avg
+        self.Unorm_factor = nf
+
+    def _normalize_Sx(self, size: bool = True, log: bool = True, pcount: float = 1, relative_size=None,
+                      target_size=None) -> None:
+        """analysis.py:586-601 (``if relative_size:`` -- truthiness, as in the reference)."""
+        cs, avg, nf = self._size_log_normalize("Sx", size, log, pcount, relative_size if relative_size else None,
+                                               target_size, False, "Sx_sz", "Sx_norm")
+        if size:
+            self.xcell_size, self.xavg_size = cs, avg
+        self.xnorm_factor = nf
+
+    def _normalize_Ux(self, size: bool = True, log: bool = True, pcount: float = 1, use_Sx_size: bool = False,
+                      relative_size=None, target_size=None) -> None:
+        """analysis.py:603-633 (the ``hasattr(self, "cell_size")`` test guarding ``xcell_size`` is the reference's)."""
+        given = None
+        if size:
+            if use_Sx_size:
+                given = self.xcell_size if hasattr(self, "cell_size") else self._host_or_dev_sums("Sx")
+            elif type(relative_size) is np.ndarray:
+                given = relative_size
+        cs, avg, nf = self._size_log_normalize("Ux", size, log, pcount, given, target_size, True, "Ux_sz", "Ux_norm")
+        if size:
+            self.xUcell_size, self.xUavg_size = cs, avg
+        self.xUnorm_factor = nf
+
+    def _host_or_dev_sums(self, name: str) -> np.ndarray:
+        from . import device as dev
+        return dev.cell_sums(self._dev(name)).cpu().numpy()
+
+    def normalize(self, which: str = "both", size: bool = True, log: bool = True, pcount: float = 1,
+                  relative_size: np.ndarray = None, use_S_size_for_U: bool = False,
+                  target_size: Tuple[float, float] = (None, None)) -> None:
+        """Normalization interface (analysis.py:635-676): creates ``S_sz``/``S_norm``, ``U_sz``/``U_norm`` or the
+        ``Sx``/``Ux`` twins; the matrices stay on the device."""
+        if which == "both":
+            self._normalize_S(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
+            self._normalize_U(size=size, log=log, pcount=pcount, use_S_size=use_S_size_for_U,
+                              relative_size=relative_size, target_size=target_size[1])
+        if "S" == which:
+            self._normalize_S(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
+        if "U" == which:
+            self._normalize_U(size=size, log=log, pcount=pcount, use_S_size=use_S_size_for_U,
+                              relative_size=relative_size, target_size=target_size[1])
+        if which == "imputed":
+            self._normalize_Sx(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
+            self._normalize_Ux(size=size, log=log, pcount=pcount, use_Sx_size=use_S_size_for_U,
+                               relative_size=relative_size, target_size=target_size[1])
+        if "Sx" == which:
+            self._normalize_Sx(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
+        if "Ux" == which:
+            self._normalize_Ux(size=size, log=log, pcount=pcount, use_Sx_size=use_S_size_for_U,
+                               relative_size=relative_size, target_size=target_size[1])
+
     # ------------------------------------------------------------------ knn_imputation (analysis.py:933-1023)
     def knn_imputation(self, k: int = None, pca_space: float = True, metric: str = "euclidean", diag: float = 1,
                        n_pca_dims: int = None, maximum: bool = False, size_norm: bool = True,
@@ -261,24 +364,16 @@ class VelocytoLoom:
         """Weight matrix of the least-squares fit (analysis.py:1179-1219) as a device matrix.
 
         The per-gene percentiles (np.percentile, linear interpolation) are order statistics over the cell
-        axis: they are found by a radix-select kernel on the device (``velo_dev_fit_weights``).  Only the
-        rarely used "maxmin_weighted" mode and user-supplied arrays go through the host."""
+        axis: they are found by a radix-select kernel on the device (``velo_dev_fit_weights_ex``).  Only
+        user-supplied weight arrays come from the host."""
         from . import device as dev
         if isinstance(weights, np.ndarray):
             return dev.CellMajor.from_gene_major(weights)
-        if weights in dev.WEIGHT_KINDS:
-            diag = weights in ("maxmin_diag", "maxmin_double")
-            return dev.fit_weights(weights, self._dev(nS), self._dev(nU), self._dev("Sx") if diag else None,
-                                   self._dev("Ux") if diag else None, maxmin_perc)
-        if weights != "maxmin_weighted":
+        if weights not in dev.WEIGHT_KINDS:
             raise ValueError(f"unknown weights={weights!r}")
-        tmpS, tmpU = getattr(self, nS), getattr(self, nU)
-        down, up = np.percentile(tmpS, maxmin_perc, 1)                                   # analysis.py:1186-1192
-        R = np.clip(tmpS, down[:, None], up[:, None])
-        R -= R.min(1)[:, None]
-        R /= R.max(1)[:, None]
-        W = 0.5 * (R ** maxmin_weighted_pow + (1 - R) ** maxmin_weighted_pow)
-        return dev.CellMajor.from_gene_major(W)
+        diag = weights in ("maxmin_diag", "maxmin_double")
+        return dev.fit_weights(weights, self._dev(nS), self._dev(nU), self._dev("Sx") if diag else None,
+                               self._dev("Ux") if diag else None, maxmin_perc, maxmin_weighted_pow)
 
     # ------------------------------------------------------------------ predict_U .. extrapolate (analysis.py:1321-1439)
     def _gamma_q(self, which_gamma: str, which_offset: Optional[str]):

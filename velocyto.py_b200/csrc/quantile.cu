@@ -241,6 +241,23 @@ __global__ void __launch_bounds__(256) k_threshold_weights(const float *__restri
     }
 }
 
+// "maxmin_weighted" (analysis.py:1186-1192): R = (clip(S, down, up) - down) / (up - down), W = (R^p + (1 - R)^p) / 2.
+// (min / max of the clipped row are the two percentiles themselves; up == down divides 0 by 0 like the reference.)
+__global__ void __launch_bounds__(256) k_smooth_weights(const float *__restrict__ X, int64_t ld,
+                                                        const double *__restrict__ thr /*G x 2*/, double power,
+                                                        float *__restrict__ W, int64_t ldw, int64_t G, int64_t C)
+{
+    const int64_t total = C * G;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t c = t / G, g = t - c * G;
+        const double down = thr[2 * g], up = thr[2 * g + 1];
+        const double x = fmin(fmax(static_cast<double>(X[c * ld + g]), down), up);
+        const double r = (x - down) / (up - down);
+        W[c * ldw + g] = static_cast<float>(0.5 * (pow(r, power) + pow(1.0 - r, power)));
+    }
+}
+
 }  // namespace velo
 
 using namespace velo;
@@ -268,12 +285,19 @@ struct Tmp {
 };
 }  // namespace
 
-// kind: 0 maxmin_diag, 1 maxmin, 2 maxmin_double, 3 sum, 4 prod   (analysis.py:1181-1219)
+// kind: 0 maxmin_diag, 1 maxmin, 2 maxmin_double, 3 sum, 4 prod, 5 maxmin_weighted   (analysis.py:1181-1219)
 extern "C" int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_cm, const float *Sx_cm,
                                     const float *Ux_cm, int64_t ld, int64_t G, int64_t C, double perc_lo,
                                     double perc_hi, float *W_cm, int64_t ldw, velo_stream_t stream)
 {
-    VELO_REQUIRE(kind >= 0 && kind <= 4, "fit_weights: unknown kind %d", kind);
+    return velo_dev_fit_weights_ex(kind, S_cm, U_cm, Sx_cm, Ux_cm, ld, G, C, perc_lo, perc_hi, 15.0, W_cm, ldw, stream);
+}
+
+extern "C" int velo_dev_fit_weights_ex(int kind, const float *S_cm, const float *U_cm, const float *Sx_cm,
+                                       const float *Ux_cm, int64_t ld, int64_t G, int64_t C, double perc_lo,
+                                       double perc_hi, double power, float *W_cm, int64_t ldw, velo_stream_t stream)
+{
+    VELO_REQUIRE(kind >= 0 && kind <= 5, "fit_weights: unknown kind %d", kind);
     VELO_REQUIRE(S_cm && U_cm && W_cm && G > 0 && C > 0 && ld >= G && ldw >= G, "fit_weights: bad arguments");
     VELO_REQUIRE((kind != 0 && kind != 2) || (Sx_cm && Ux_cm), "fit_weights: maxmin_diag needs Sx and Ux");
     cudaStream_t st = as_stream(stream);
@@ -311,6 +335,13 @@ extern "C" int velo_dev_fit_weights(int kind, const float *S_cm, const float *U_
         return VELO_OK;
     };
     if (kind == 1) return thresholds(S_cm, 0);                                       // "maxmin"  :1193-1195
+    if (kind == 5) {                                                                 // "maxmin_weighted" :1186-1192
+        if ((rc = velo_dev_unpack_genemajor(S_cm, ld, G, C, rows_p, 4, stream))) return rc;
+        if ((rc = velo_dev_row_percentiles(rows_p, G, C, q_p + 1, 2, thr_p, stream))) return rc;
+        k_smooth_weights<<<eg, 256, 0, st>>>(S_cm, ld, thr_p, power, W_cm, ldw, G, C);
+        VELO_LAUNCH_CHECK();
+        return VELO_OK;
+    }
     if (kind == 0 || kind == 2) {                                                    // "maxmin_diag" :1196-1207
         if ((rc = denominators(Sx_cm, invS_p))) return rc;
         if ((rc = denominators(Ux_cm, invU_p))) return rc;

@@ -329,8 +329,29 @@ def embedding_shift(tp: torch.Tensor, ixs: torch.Tensor, embedding, c0: int = 0)
     return out
 
 
+# --------------------------------------------------------------------------- normalisation (analysis.py:535-676)
+def cell_sums(X: CellMajor) -> torch.Tensor:
+    """``X.sum(0)`` of the reference's gene-major matrix: per-cell totals, float64 CUDA vector."""
+    out = torch.empty(X.C, dtype=torch.float64, device=X.t.device)
+    _cabi.call("velo_dev_cell_sums", X.ptr, X.ld, X.G, X.C, out.data_ptr(), _stream_ptr())
+    return out
+
+
+def size_normalize(X: CellMajor, factor: Optional[torch.Tensor], pcount: float = 1.0, want_sz: bool = True,
+                   want_norm: bool = True, nonfinite_to_zero: bool = False):
+    """``(factor * X, log2(factor * X + pcount))`` in one pass; ``factor``: per-cell float64 CUDA vector or None."""
+    sz = CellMajor(torch.empty_like(X.t), X.G) if want_sz else None
+    nm = CellMajor(torch.empty_like(X.t), X.G) if want_norm else None
+    if factor is not None:
+        assert factor.is_cuda and factor.dtype == torch.float64 and factor.numel() == X.C and factor.is_contiguous()
+    _cabi.call("velo_dev_size_normalize", X.ptr, X.ld, X.G, X.C, 0 if factor is None else factor.data_ptr(),
+               float(pcount), int(bool(nonfinite_to_zero)), 0 if sz is None else sz.ptr, 0 if nm is None else nm.ptr,
+               _stream_ptr())
+    return sz, nm
+
+
 # --------------------------------------------------------------------------- fit_gammas weights (analysis.py:1179-1219)
-WEIGHT_KINDS = {"maxmin_diag": 0, "maxmin": 1, "maxmin_double": 2, "sum": 3, "prod": 4}
+WEIGHT_KINDS = {"maxmin_diag": 0, "maxmin": 1, "maxmin_double": 2, "sum": 3, "prod": 4, "maxmin_weighted": 5}
 
 
 def row_percentiles(M: CellMajor, q) -> torch.Tensor:
@@ -345,12 +366,12 @@ def row_percentiles(M: CellMajor, q) -> torch.Tensor:
 
 
 def fit_weights(kind: str, S: CellMajor, U: CellMajor, Sx: Optional[CellMajor] = None, Ux: Optional[CellMajor] = None,
-                maxmin_perc=(2, 98)) -> CellMajor:
+                maxmin_perc=(2, 98), maxmin_weighted_pow: float = 15) -> CellMajor:
     """Weight matrix of the gamma fit built on the device (per-gene radix-select percentiles)."""
     W = CellMajor.empty(S.C, S.G, S.t.device)
-    _cabi.call("velo_dev_fit_weights", WEIGHT_KINDS[kind], S.ptr, U.ptr, 0 if Sx is None else Sx.ptr,
+    _cabi.call("velo_dev_fit_weights_ex", WEIGHT_KINDS[kind], S.ptr, U.ptr, 0 if Sx is None else Sx.ptr,
                0 if Ux is None else Ux.ptr, S.ld, S.G, S.C, float(maxmin_perc[0]), float(maxmin_perc[1]),
-               W.ptr, W.ld, _stream_ptr())
+               float(maxmin_weighted_pow), W.ptr, W.ld, _stream_ptr())
     return W
 
 
