@@ -169,7 +169,7 @@ class VelocytoLoom:
                 warnings.simplefilter("ignore")
                 with np.errstate(divide="ignore", invalid="ignore"):
                     norm_factor = avg_size / cell_size
-            fac = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(norm_factor, (X.C,)), dtype=np.float64)).to(X.t.device)
+            fac = torch.from_numpy(np.array(np.broadcast_to(norm_factor, (X.C,)), dtype=np.float64)).to(X.t.device)
         else:
             avg_size, norm_factor, fac = None, 1, None
         sz, nm = dev.size_normalize(X, fac, pcount, want_sz=True, want_norm=bool(log), nonfinite_to_zero=guard)

@@ -36,9 +36,9 @@ __global__ void __launch_bounds__(256) k_size_normalize(const float *__restrict_
 {
     const int64_t c = blockIdx.x;
     const double f = factor ? factor[c] : 1.0;
-    const int64_t G4 = (G + 3) >> 2;
-    for (int64_t q = threadIdx.x; q < G4; q += blockDim.x) {
-        const int64_t off = c * ld + (q << 2);                 // ld % 4 == 0: a started quad is inside the row
+    const int64_t L4 = ld >> 2;                                // whole row incl. the pad columns (written as zeros)
+    for (int64_t q = threadIdx.x; q < L4; q += blockDim.x) {
+        const int64_t off = c * ld + (q << 2);
         const float4 v = *reinterpret_cast<const float4 *>(X + off);
         const float in[4] = {v.x, v.y, v.z, v.w};
         float sz[4], nm[4];
