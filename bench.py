@@ -289,6 +289,31 @@ def main():
                  "roofline_achieved_gbs": alg_bytes / (ms_lk * 1e-3) / 1e9, "frac": alg_bytes / (ms_lk * 1e-3) / 1e9 / peak}
         del ix_local
 
+    # ---------------- secondary: the all-pairs linear variant on the tensor cores (K2g, BASELINE config 3 reduced) --------
+    tensor = None
+    if not args.no_local and world == 1:
+        Cf = min(16384, core.nc)
+        ef, df = e_loc.rows(0, Cf), d_loc.rows(0, Cf)
+        st_f = dev.cell_stats(df)
+        out_f = torch.empty((Cf, Cf), dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            dev.coldeltacor_linear_tc(ef, df, stats=st_f, out=out_f)
+        torch.cuda.synchronize()
+        ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ta.record()
+        for _ in range(3):
+            dev.coldeltacor_linear_tc(ef, df, stats=st_f, out=out_f)
+        tb.record()
+        torch.cuda.synchronize()
+        ms_f = ta.elapsed_time(tb) / 3
+        tflops = 12.0 * G * Cf * Cf / (ms_f * 1e-3) / 1e12
+        tpeak = float(json.load(open(peaks_path)).get("bf16_tflops", 1590.0)) if os.path.exists(peaks_path) else 1590.0
+        tensor = {"workload": f"colDeltaCor all-pairs linear, {Cf} cells x {G} genes (k_coldeltacor_tc2, tcgen05 cta_group::2)",
+                  "ms": ms_f, "cells_per_s": Cf / (ms_f * 1e-3),
+                  "roofline": {"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                               "flop_model": "12 flop per pair-gene (P = B X^T, Q = X X^T; hi*hi + hi*lo + lo*hi in fp16)"}}
+        del out_f
+
     # ---------------- e2e: host buffers through the C ABI (N == 1) / the sharded host API (N > 1) -------
     e2e = None
     if not args.no_e2e:
@@ -314,7 +339,7 @@ def main():
                        "l2": "inputs (12 GB expression matrix, random row gather) exceed the 126 MB L2; no flush needed",
                        "step": "all-gather(e) [N>1] + cell_stats + k_coldeltacor + transition_prob"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
-            "secondary_local_neighbours": local,
+            "secondary_local_neighbours": local, "secondary_full_linear_tensor": tensor,
         }
         print(json.dumps(line))
     if world > 1:

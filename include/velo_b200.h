@@ -292,6 +292,20 @@ int velo_dev_knn_smooth_csr(const int64_t *w_indptr, const int32_t *w_indices, c
 int velo_dev_knn(const double *X, int64_t C, int D, int k, int include_self,
                  int32_t *out_idx, double *out_dist, velo_stream_t stream);
 
+/* ---- device-side randomisation (opt-in; the default keeps the reference's NumPy / numba streams on the host) ----
+ * Weighted sampling without replacement of m of the W candidate neighbours of every cell (analysis.py:1552-1566, one
+ * np.random.choice(W, m, replace=False, p) per cell): same distribution (successive sampling, order included) through
+ * exponential-clock keys -log(u) / p and a per-cell sort; Philox4x32-10 stream keyed by (seed, cell, candidate).
+ * knn_idx: C x W int32 candidate cells (row = kNN order); inv_p: W floats 1 / p_j (p_j > 0);
+ * outputs C x m int32: sampling_ixs = chosen positions, neigh_ixs = knn_idx[c, sampling_ixs[c, :]]. */
+int velo_dev_sample_neighbors(const int32_t *knn_idx, int64_t C, int W, const float *inv_p, int m, uint64_t seed,
+                              int32_t *neigh_ixs, int32_t *sampling_ixs, velo_stream_t stream);
+/* Randomised control permute_rows_nsign (analysis.py:2413-2420) in the cell-major layout: out[c, g] = +-in[pi_g(c), g],
+ * an independent pseudo-random permutation of the cells and independent signs for every gene (Feistel bijection, no
+ * sort).  in != out. */
+int velo_dev_permute_rows_nsign(const float *in_cm, float *out_cm, int64_t ld, int64_t G, int64_t C, uint64_t seed,
+                                velo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

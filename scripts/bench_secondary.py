@@ -70,6 +70,19 @@ def main():
     t0 = time.perf_counter(); dev.knn(pcs, k); torch.cuda.synchronize(); t1 = time.perf_counter()
     print(json.dumps(dict(kernel=f"k_knn_bruteforce {C} points x 20-D, k={k} (knn_imputation search)", ms=(t1 - t0) * 1e3)))
     del pts, pcs
+    # device-side randomisation at BASELINE config 4 scale (opt-in random_backend="device")
+    Cs, W, m = 100_000, 10_001, 3_000
+    knn_idx = torch.randint(0, Cs, (Cs, W), device="cuda", dtype=torch.int32, generator=gen)
+    p = np.linspace(0.5, 0.1, W); p /= p.sum()
+    ms = timeit(lambda: dev.sample_neighbors(knn_idx, p, m, 1), iters=3, warm=1)
+    print(json.dumps(dict(kernel=f"k_sample_neighbors {Cs} cells, {m} of {W} candidates (replaces the per-cell np.random.choice loop)", ms=ms)))
+    del knn_idx
+    Gs = 30_000
+    dS = dev.CellMajor.empty(Cs // 2, Gs)
+    dS.t.normal_(generator=gen)
+    ms = timeit(lambda: dev.permute_rows_nsign(dS, 1), iters=3, warm=1)
+    report(f"k_permute_rows_nsign {Cs // 2} cells x {Gs} genes (randomised control)", ms, 2 * (Cs // 2) * Gs * 4)
+    del dS
     # full (all pairs) correlation, reduced config 3: G=30k, C=4k -> G*C^2 = 4.8e11 elements
     del S, U, Ux, W, src, dst
     Cf, Gf = 4000, 30_000

@@ -524,3 +524,85 @@ def test_normalize_medium_matches_oracle(oracle):
         np.testing.assert_allclose(sz.to_gene_major(), want_sz, rtol=2e-7, atol=0, equal_nan=True)
         np.testing.assert_allclose(nm.to_gene_major(), want_nm, rtol=2e-7, atol=2e-7, equal_nan=True)
         assert float(sz.t[:, G:].abs().sum()) == 0.0 and float(nm.t[:, G:].abs().sum()) == 0.0   # pad columns stay zero
+
+
+# ----------------------------------------------------------------------------------------------------------
+# device-side randomisation (opt-in random_backend="device"; analysis.py:1552-1566, 2413-2420)
+
+def test_device_neighbour_sampler_structure_and_distribution():
+    """velo_dev_sample_neighbors draws from the distribution of np.random.choice(W, m, replace=False, p) -- successive
+    sampling without replacement, order included -- with its own (Philox) stream: rows are distinct positions, the
+    gathered ids match, the first pick follows p, and the per-position inclusion frequencies match a NumPy simulation."""
+    import torch
+    from velocyto_b200 import device as dev
+    C, W, m = 20000, 61, 18
+    rng = np.random.default_rng(5)
+    knn_idx = torch.from_numpy(rng.integers(0, C, (C, W)).astype(np.int32)).cuda()
+    p = np.linspace(0.5, 0.1, W)
+    p /= p.sum()
+    neigh, samp = dev.sample_neighbors(knn_idx, p, m, 15071990)
+    neigh2, samp2 = dev.sample_neighbors(knn_idx, p, m, 15071990)
+    assert torch.equal(samp, samp2) and torch.equal(neigh, neigh2)                   # deterministic for a seed
+    _, samp3 = dev.sample_neighbors(knn_idx, p, m, 7)
+    assert not torch.equal(samp, samp3)
+    s = samp.cpu().numpy()
+    assert s.min() >= 0 and s.max() < W
+    assert all(len(set(row)) == m for row in s[:2000])                               # without replacement
+    assert np.array_equal(neigh.cpu().numpy(), knn_idx.cpu().numpy()[np.arange(C)[:, None], s])
+    first = np.bincount(s[:, 0], minlength=W) / C                                    # first pick ~ p
+    assert np.abs(first - p).max() < 4 * np.sqrt(p.max() / C)
+    incl = np.zeros(W)
+    np.add.at(incl, s.ravel(), 1.0)
+    incl /= C
+    np.random.seed(1)                                                                # the reference's sampler, simulated
+    ref = np.zeros(W)
+    n_ref = 6000
+    for _ in range(n_ref):
+        ref[np.random.choice(W, size=(m,), replace=False, p=p)] += 1.0
+    ref /= n_ref
+    assert np.abs(incl - ref).max() < 5 * np.sqrt(0.25 / n_ref)
+    # a row wider than one warp-sized sort and not a power of two; m == W returns a permutation of all positions
+    _, full = dev.sample_neighbors(knn_idx[:50, :37].contiguous(), np.full(37, 1 / 37), 37, 3)
+    assert np.array_equal(np.sort(full.cpu().numpy(), axis=1), np.tile(np.arange(37), (50, 1)))
+
+
+def test_device_permute_rows_nsign():
+    """Every gene row is an independent permutation of the cells with random signs (analysis.py:2413-2420)."""
+    from velocyto_b200 import device as dev
+    G, C = 37, 1000
+    rng = np.random.default_rng(8)
+    X = (rng.normal(size=(G, C)) + 3.0 * np.arange(C)[None, :]).astype(np.float32).astype(np.float64)   # distinct |values|
+    Xd = dev.CellMajor.from_gene_major(X)
+    Y = dev.permute_rows_nsign(Xd, 99).to_gene_major()
+    assert np.array_equal(Y, dev.permute_rows_nsign(Xd, 99).to_gene_major())
+    assert np.array_equal(np.sort(np.abs(Y), axis=1), np.sort(np.abs(X), axis=1))    # a permutation of every row
+    assert not np.array_equal(np.abs(Y), np.abs(X))
+    neg = (Y < 0).mean()                                                             # X > 0 almost everywhere
+    assert 0.45 < neg < 0.55
+    perms = np.argsort(np.abs(Y), axis=1)                                            # where each rank went, per gene
+    assert len({tuple(r[:20]) for r in perms}) == G                                  # genes are permuted independently
+    fixed = (np.abs(Y) == np.abs(X)).mean()
+    assert fixed < 5.0 / C + 0.01                                                    # ~1/C fixed points
+
+
+def test_estimate_transition_prob_device_random_backend(golden):
+    """The opt-in device backend runs the whole method without host RNG loops and yields a valid result of the same
+    shape; with the sampled neighbours handed to the oracle the correlations agree."""
+    from velocyto_b200.analysis import VelocytoLoom
+    from oracle import velo_oracle as vo
+    g = golden("pipeline_small.npz")
+    vlm = VelocytoLoom(S=g["S_sz"].copy(), U=g["U_sz"].copy())
+    vlm.Sx_sz, vlm.delta_S, vlm.used_delta_t = g["Sx_sz"].copy(), g["delta_S"].copy(), 1.0
+    vlm.ts = g["embedding"].copy()
+    C = vlm.ts.shape[0]
+    vlm.estimate_transition_prob(hidim="Sx_sz", embed="ts", transform="sqrt", psc=1, n_neighbors=30, knn_random=True,
+                                 sampled_fraction=0.5, random_backend="device")
+    m = int(0.5 * 31)
+    assert vlm.sampling_ixs.shape == (C, m) and vlm.neigh_ixs.shape == (C, m)
+    assert vlm.corrcoef.shape == (C, C) and vlm.corrcoef_random.shape == (C, C)
+    assert np.array_equal(np.sort(np.abs(vlm.delta_S_rndm), axis=1), np.sort(np.abs(g["delta_S"].astype(np.float32).astype(np.float64)), axis=1))
+    d = vo.velocity_transform(g["delta_S"], "sqrt", 1.0)
+    want = vo.coldeltacor(np.ascontiguousarray(g["Sx_sz"]), np.ascontiguousarray(d), vlm.neigh_ixs, "sqrt", 1.0)
+    want = vo.patch_corrcoef(want)
+    rows = np.arange(C)[:, None]
+    np.testing.assert_allclose(vlm.corrcoef[rows, vlm.neigh_ixs], want[rows, vlm.neigh_ixs], rtol=0, atol=5e-6)

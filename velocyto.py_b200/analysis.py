@@ -454,6 +454,12 @@ class VelocytoLoom:
         from sklearn.neighbors import NearestNeighbors
         from . import device as dev
         dense_limit = kwargs.pop("dense_limit", 20000)
+        # "reference" (default): the reference's NumPy / numba random streams on the host -- bit-equal sampling_ixs and
+        # delta_S_rndm, but a Python loop of np.random.choice per cell and a numba shuffle per gene (tens of seconds at
+        # 100k cells).  "device": the same distributions drawn by velo_dev_sample_neighbors / velo_dev_permute_rows_nsign.
+        random_backend = kwargs.pop("random_backend", "reference")
+        if random_backend not in ("reference", "device"):
+            raise ValueError("random_backend must be 'reference' or 'device'")
         for stale in ("_corrcoef_random_dev", "corrcoef_random", "corrcoef_random_compact"):
             self.__dict__.pop(stale, None)
         _numba_seed(random_seed)                                                         # analysis.py:1501
@@ -510,32 +516,46 @@ class VelocytoLoom:
         d_cm = transformed(dS)
         d_rnd = None
         if calculate_randomized:                                                         # analysis.py:1539-1542
-            rnd = np.copy(self.delta_S)
-            _permute_rows_nsign(rnd)
-            self.delta_S_rndm = rnd
+            if random_backend == "device":
+                self._set_dev("delta_S_rndm", dev.permute_rows_nsign(dS, random_seed))
+            else:
+                rnd = np.copy(self.delta_S)
+                _permute_rows_nsign(rnd)
+                self.delta_S_rndm = rnd
             d_rnd = transformed(self._dev("delta_S_rndm"))
         embedding = getattr(self, embed)
         self.embedding = embedding
-        if n_neighbors + 1 <= dev.KNN_MAX_K:                                             # analysis.py:1547-1549, on the device
+        knn_idx_dev = None
+        if knn_random and random_backend == "device" and n_neighbors + 1 <= dev.KNN_MAX_K:
+            knn_idx_dev, _ = dev.knn(np.ascontiguousarray(embedding, dtype=np.float64), n_neighbors + 1, False)
+        elif n_neighbors + 1 <= dev.KNN_MAX_K:                                           # analysis.py:1547-1549, on the device
             self.embedding_knn = knn_graph_device(np.asarray(embedding), n_neighbors + 1, "connectivity")
         else:
             nn = NearestNeighbors(n_neighbors=n_neighbors + 1, n_jobs=n_jobs)
             nn.fit(embedding)
             self.embedding_knn = nn.kneighbors_graph(mode="connectivity")
         if knn_random:
-            neigh_ixs = self.embedding_knn.indices.reshape((-1, n_neighbors + 1))
-            p = np.linspace(sampling_probs[0], sampling_probs[1], neigh_ixs.shape[1])
+            p = np.linspace(sampling_probs[0], sampling_probs[1], n_neighbors + 1)
             p = p / p.sum()
             size = int(sampled_fraction * (n_neighbors + 1))
-            sampling_ixs = np.stack([np.random.choice(neigh_ixs.shape[1], size=(size,), replace=False, p=p)
-                                     for _ in range(neigh_ixs.shape[0])], 0)             # analysis.py:1561-1564
-            self.sampling_ixs = sampling_ixs
-            neigh_ixs = neigh_ixs[np.arange(neigh_ixs.shape[0])[:, None], sampling_ixs]
+            if random_backend == "device":
+                if knn_idx_dev is None:
+                    knn_idx_dev = torch.from_numpy(np.ascontiguousarray(
+                        self.embedding_knn.indices.reshape((-1, n_neighbors + 1)), dtype=np.int32)).to(dev.require_cuda())
+                ix_dev, samp_dev = dev.sample_neighbors(knn_idx_dev.contiguous(), p, size, random_seed)
+                self.sampling_ixs = samp_dev.cpu().numpy().astype(np.intp)
+                neigh_ixs = ix_dev.cpu().numpy().astype(np.intp)
+            else:
+                neigh_ixs = self.embedding_knn.indices.reshape((-1, n_neighbors + 1))
+                sampling_ixs = np.stack([np.random.choice(neigh_ixs.shape[1], size=(size,), replace=False, p=p)
+                                         for _ in range(neigh_ixs.shape[0])], 0)         # analysis.py:1561-1564
+                self.sampling_ixs = sampling_ixs
+                neigh_ixs = neigh_ixs[np.arange(neigh_ixs.shape[0])[:, None], sampling_ixs]
             nonzero = neigh_ixs.shape[0] * neigh_ixs.shape[1]
             self.embedding_knn = sparse.csr_matrix((np.ones(nonzero), neigh_ixs.ravel(),
                                                     np.arange(0, nonzero + 1, neigh_ixs.shape[1])),
                                                    shape=(neigh_ixs.shape[0], neigh_ixs.shape[0]))
-            ix = dev.indices_to_device(neigh_ixs, C)
+            ix = ix_dev if random_backend == "device" else dev.indices_to_device(neigh_ixs, C)
             self.neigh_ixs = neigh_ixs
         else:
             ix = None

@@ -1,0 +1,149 @@
+// Device-side randomisation for estimate_transition_prob (opt-in, `random_backend="device"`):
+//   * the per-cell weighted neighbour sampler of analysis.py:1552-1566 -- one legacy
+//     `np.random.choice(n+1, size, replace=False, p=p)` per cell in a Python loop (0.3-0.5 ms per cell: tens of seconds
+//     at 100k cells, an order of magnitude more than the correlation kernel it feeds);
+//   * the randomised control `permute_rows_nsign` (analysis.py:2413-2420): every gene row shuffled and sign-flipped.
+// NumPy's algorithm keeps the first occurrences of an i.i.d. stream drawn from p and renormalises -- i.e. successive
+// sampling without replacement (Plackett-Luce).  The same distribution, order included, is obtained by giving every
+// candidate an exponential clock key = -log(u) / p and taking the `size` smallest keys in ascending order
+// (Efraimidis-Spirakis); that is what the kernel does, with a counter-based Philox4x32-10 stream per (seed, cell,
+// candidate).  The RANDOM STREAM differs from NumPy's MT19937 -- which is why the default backend stays the host one
+// (bit-equal `sampling_ixs` / `delta_S_rndm`, tested against the reference's golden vectors).
+#include "velo_common.cuh"
+
+namespace velo {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x)   // murmur3 finaliser
+{
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
+// one CTA per cell: keys for the W candidates, bitonic sort of (key, position) in shared memory, first m win
+__global__ void __launch_bounds__(1024) k_sample_neighbors(const int32_t *__restrict__ knn_idx, int64_t C, int W,
+                                                           const float *__restrict__ inv_p, int m, uint64_t seed, int Np,
+                                                           int32_t *__restrict__ neigh_ixs, int32_t *__restrict__ sampling_ixs)
+{
+    extern __shared__ unsigned long long keys[];
+    const int64_t cell = blockIdx.x;
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    for (int j4 = threadIdx.x; 4 * j4 < Np; j4 += blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(cell), static_cast<uint32_t>(cell >> 32),
+                                                 static_cast<uint32_t>(j4), 0x53414d50u /* "SAMP" */), key);
+        const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = 4 * j4 + k;
+            unsigned long long packed = ~0ull;
+            if (j < W) {
+                const float u = (static_cast<float>(rv[k] >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+                const float t = -__logf(u) * inv_p[j];                                           // exponential clock
+                packed = (static_cast<unsigned long long>(__float_as_uint(t)) << 32) | static_cast<uint32_t>(j);
+            }
+            keys[j] = packed;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= Np; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (Np >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const unsigned long long a = keys[i], b = keys[l];
+                if ((a > b) == ((i & k) == 0)) {
+                    keys[i] = b;
+                    keys[l] = a;
+                }
+            }
+            __syncthreads();
+        }
+    for (int n = threadIdx.x; n < m; n += blockDim.x) {
+        const int pos = static_cast<int>(keys[n] & 0xffffffffu);
+        sampling_ixs[cell * m + n] = pos;
+        neigh_ixs[cell * m + n] = knn_idx[cell * W + pos];
+    }
+}
+
+// out[c, g] = +-in[pi_g(c), g]: pi_g = 4-round Feistel bijection on [0, 4^h) >= C keyed by (seed, g), cycle-walked into
+// [0, C); the sign is an independent hash bit of (seed, g, c)
+__global__ void __launch_bounds__(256) k_permute_rows_nsign(const float *__restrict__ in, float *__restrict__ out,
+                                                            int64_t ld, int64_t G, int64_t C, uint64_t seed, int h)
+{
+    const uint32_t mask = (1u << h) - 1u;
+    const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+    const int64_t total = C * G;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t c = t / G, g = t - c * G;
+        const uint32_t kg = mix32(static_cast<uint32_t>(g) ^ s0) + s1;
+        uint32_t x = static_cast<uint32_t>(c);
+        do {
+            uint32_t L = x >> h, R = x & mask;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t f = mix32(R + kg * (2u * r + 1u) + 0x9E3779B9u * (r + 1u)) & mask;
+                const uint32_t nl = R;
+                R = L ^ f;
+                L = nl;
+            }
+            x = (L << h) | R;
+        } while (x >= static_cast<uint32_t>(C));
+        const uint32_t sbit = mix32(static_cast<uint32_t>(c) * 0x9E3779B1u ^ mix32(kg ^ 0x5bd1e995u)) & 1u;
+        const float v = in[static_cast<int64_t>(x) * ld + g];
+        out[c * ld + g] = sbit ? -v : v;
+    }
+}
+
+}  // namespace velo
+
+using namespace velo;
+
+extern "C" int velo_dev_sample_neighbors(const int32_t *knn_idx, int64_t C, int W, const float *inv_p, int m,
+                                         uint64_t seed, int32_t *neigh_ixs, int32_t *sampling_ixs, velo_stream_t stream)
+{
+    VELO_REQUIRE(knn_idx && inv_p && neigh_ixs && sampling_ixs, "sample_neighbors: null pointer");
+    VELO_REQUIRE(C >= 0 && W > 0 && m >= 0 && m <= W, "sample_neighbors: need 0 <= m <= W");
+    VELO_REQUIRE(C < (1LL << 31), "sample_neighbors: too many cells for one launch");
+    if (C == 0 || m == 0) return VELO_OK;
+    int Np = 64;
+    while (Np < W) Np <<= 1;
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const size_t smem = static_cast<size_t>(Np) * 8;
+    VELO_REQUIRE(smem <= static_cast<size_t>(dp.smem_optin), "sample_neighbors: at most %d candidates per cell (got %d)",
+                 dp.smem_optin / 8, W);
+    VELO_CUDA_TRY(cudaFuncSetAttribute(k_sample_neighbors, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    const int threads = Np / 2 >= 1024 ? 1024 : (Np / 2 < 64 ? 64 : Np / 2);
+    k_sample_neighbors<<<static_cast<unsigned>(C), threads, smem, as_stream(stream)>>>(knn_idx, C, W, inv_p, m, seed, Np,
+                                                                                     neigh_ixs, sampling_ixs);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+extern "C" int velo_dev_permute_rows_nsign(const float *in_cm, float *out_cm, int64_t ld, int64_t G, int64_t C,
+                                           uint64_t seed, velo_stream_t stream)
+{
+    VELO_REQUIRE(in_cm && out_cm && in_cm != out_cm && G > 0 && C > 0 && ld >= G, "permute_rows_nsign: bad arguments");
+    VELO_REQUIRE(C < (1LL << 30), "permute_rows_nsign: too many cells");
+    int h = 1;
+    while ((1LL << (2 * h)) < C) ++h;
+    const int64_t nblk = (C * G + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(nblk < 148LL * 64 ? nblk : 148LL * 64);
+    k_permute_rows_nsign<<<grid, 256, 0, as_stream(stream)>>>(in_cm, out_cm, ld, G, C, seed, h);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}

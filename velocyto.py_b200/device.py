@@ -440,3 +440,32 @@ def knn(points, k: int, include_self: bool = False):
     _cabi.call("velo_dev_knn", X.data_ptr(), C, D, int(k), int(bool(include_self)), idx.data_ptr(), dist.data_ptr(),
                _stream_ptr())
     return idx, dist
+
+
+# --------------------------------------------------------------------------- device-side randomisation (opt-in)
+def sample_neighbors(knn_idx: torch.Tensor, p, m: int, seed: int):
+    """Weighted sampling without replacement of ``m`` of the ``W`` candidates of every cell on the device
+    (``velo_dev_sample_neighbors``): the distribution of ``np.random.choice(W, m, replace=False, p=p)`` per cell
+    (analysis.py:1561-1564), not its MT19937 stream.  Returns ``(neigh_ixs, sampling_ixs)``, ``(C, m)`` int32 CUDA."""
+    assert knn_idx.is_cuda and knn_idx.dtype == torch.int32 and knn_idx.dim() == 2 and knn_idx.is_contiguous()
+    C, W = knn_idx.shape
+    p = np.asarray(p, dtype=np.float64)
+    if p.shape != (W,) or not np.all(p > 0):
+        raise ValueError("p must hold one positive probability per candidate")
+    inv_p = torch.from_numpy((1.0 / p).astype(np.float32)).to(knn_idx.device)
+    neigh = torch.empty((C, m), dtype=torch.int32, device=knn_idx.device)
+    samp = torch.empty((C, m), dtype=torch.int32, device=knn_idx.device)
+    _cabi.call("velo_dev_sample_neighbors", knn_idx.data_ptr(), C, W, inv_p.data_ptr(), int(m),
+               int(seed) & 0xFFFFFFFFFFFFFFFF, neigh.data_ptr(), samp.data_ptr(), _stream_ptr())
+    return neigh, samp
+
+
+def permute_rows_nsign(X: CellMajor, seed: int) -> CellMajor:
+    """Randomised control of ``estimate_transition_prob`` (``permute_rows_nsign``, analysis.py:2413-2420) on the device:
+    every gene gets its own pseudo-random permutation of the cells and independent random signs."""
+    out = CellMajor(torch.empty_like(X.t), X.G)
+    if X.ld != X.G:
+        out.t[:, X.G:].zero_()
+    _cabi.call("velo_dev_permute_rows_nsign", X.ptr, out.ptr, X.ld, X.G, X.C, int(seed) & 0xFFFFFFFFFFFFFFFF,
+               _stream_ptr())
+    return out
