@@ -217,3 +217,25 @@ def test_connectivity_with_diagonal_equals_scipy_path():
             want.setdiag(diag)
         got = connectivity_with_diagonal(knn, diag)
         assert np.array_equal(got.toarray(), want.toarray())
+
+
+def test_integration_stub_binds_against_the_built_library():
+    """The ctypes stub INTEGRATION.md tells a maintainer to drop in as velocyto/speedboosted.py must load and bind
+    against the library as built (no compute call here: there is no GPU in this tier)."""
+    import re
+    from velocyto_b200 import _cabi
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```python\n(# velocyto/speedboosted\.py.*?)```", text, re.S)
+    assert m, "INTEGRATION.md lost its speedboosted.py stub"
+    src = m.group(1).replace('"libvelo_b200.so"', repr(_cabi.LIB_PATH))
+    ns = {}
+    exec(compile(src, "INTEGRATION.md:speedboosted.py", "exec"), ns)
+    for name in ("_colDeltaCor", "_colDeltaCorSqrt", "_colDeltaCorLog10", "_colDeltaCorpartial",
+                 "_colDeltaCorSqrtpartial", "_colDeltaCorLog10partial"):            # speedboosted.pyx:542-610
+        assert callable(ns[name]), name
+    # the typed-memoryview contract of the .pyx is kept: non-contiguous / non-float64 input is refused before any call
+    bad = np.zeros((4, 6), dtype=np.float32)
+    with pytest.raises(ValueError):
+        ns["_colDeltaCor"](bad, bad, bad, 1)
+    with pytest.raises(ValueError):
+        ns["_colDeltaCor"](np.zeros((4, 6)).T, np.zeros((6, 4)), np.zeros((6, 6)), 1)
