@@ -239,3 +239,37 @@ def test_integration_stub_binds_against_the_built_library():
         ns["_colDeltaCor"](bad, bad, bad, 1)
     with pytest.raises(ValueError):
         ns["_colDeltaCor"](np.zeros((4, 6)).T, np.zeros((6, 4)), np.zeros((6, 6)), 1)
+
+
+def test_exponential_clock_sampling_is_numpy_choice_without_replacement():
+    """The math behind the opt-in device sampler (csrc/random.cu): keeping the `size` smallest keys -log(u)/p, in ascending
+    order, has the distribution of np.random.choice(W, size, replace=False, p) -- successive sampling, order included
+    (analysis.py:1561-1564).  Checked here with NumPy on both sides: first pick, ordered (first, second) pair and
+    per-candidate inclusion frequencies."""
+    W, size, n = 7, 3, 40000
+    p = np.linspace(0.5, 0.1, W)
+    p /= p.sum()
+    rng = np.random.default_rng(0)
+    keys = -np.log(rng.uniform(size=(n, W))) / p
+    mine = np.argsort(keys, axis=1)[:, :size]
+    np.random.seed(1)
+    ref = np.stack([np.random.choice(W, size=(size,), replace=False, p=p) for _ in range(n)])
+
+    def stats(s):
+        first = np.bincount(s[:, 0], minlength=W) / n
+        pair = np.zeros((W, W))
+        np.add.at(pair, (s[:, 0], s[:, 1]), 1.0 / n)
+        incl = np.zeros(W)
+        np.add.at(incl, s.ravel(), 1.0 / n)
+        return first, pair, incl
+
+    f1, p1, i1 = stats(mine)
+    f2, p2, i2 = stats(ref)
+    tol = 5 * np.sqrt(0.25 / n)                              # 5 sigma of a frequency estimate, both sides sampled
+    assert np.abs(f1 - p).max() < tol and np.abs(f2 - p).max() < tol
+    assert np.abs(p1 - p2).max() < 2 * tol
+    assert np.abs(i1 - i2).max() < 2 * tol
+    # closed form of the ordered pair under successive sampling: p_a * p_b / (1 - p_a)
+    want = p[:, None] * p[None, :] / (1 - p[:, None])
+    np.fill_diagonal(want, 0.0)
+    assert np.abs(p1 - want).max() < tol
