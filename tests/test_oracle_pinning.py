@@ -203,3 +203,46 @@ def test_normalize_oracle_matches_golden(oracle, golden):
     check("imputed_opts", "Sx_sz", "Sx_norm", oracle.size_log_normalize(Sx, pcount=2.0, target_size=800.0))
     # use_Sx_size without a previous S normalisation: hasattr(self, "cell_size") is False -> Sx.sum(0) (analysis.py:607-610)
     check("imputed_opts", "Ux_sz", "Ux_norm", oracle.size_log_normalize(Ux, pcount=2.0, cell_size=Sx.sum(0), guard=True))
+
+
+def test_gemm_identity_and_fp16_pair_split_reproduce_linear_coldeltacor(oracle):
+    """Numerical design of the tensor-core kernel K2g (csrc/coldeltacor_tc.cu), checked on the host against the oracle:
+    (1) x_colDeltaCor (speedboosted.pyx:13-87) == the two gene-axis products P = B X^T, Q = X X^T plus the epilogue;
+    (2) scaling every operand row by a power of two and splitting it into an fp16 (hi, lo) pair, with the three
+        products hi*hi + hi*lo + lo*hi, keeps the correlation within 5e-8 -- a bf16 pair does not (> 2e-7)."""
+    import torch
+    G, C = 1500, 96
+    rng = np.random.default_rng(3)
+    level = rng.gamma(0.6, 2.0, G)[:, None] + 0.05
+    e = (rng.gamma(2.0, 1.0, (G, C)) * level).astype(np.float32).astype(np.float64)
+    d = rng.normal(size=(G, C)).astype(np.float32).astype(np.float64)
+    want = oracle.colDeltaCor(e, d)
+    off = ~np.eye(C, dtype=bool)
+    X = e - e.mean(1, keepdims=True)
+    X = (X - X.mean(0, keepdims=True)).astype(np.float32).astype(np.float64)
+    B = (d - d.mean(0, keepdims=True)).astype(np.float32).astype(np.float64)
+    qd, pcc, sbb = (X * X).sum(0), (B * X).sum(0), (B * B).sum(0)
+
+    def corr_from(P, Q):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return (P - pcc[:, None]) / np.sqrt((qd[:, None] + qd[None, :] - 2 * Q) * sbb[:, None])
+
+    # (1) -- with the centred operands rounded to fp32 as on the device (that rounding alone costs ~4e-9)
+    np.testing.assert_allclose(corr_from(B.T @ X, X.T @ X)[off], want[off], rtol=0, atol=1e-8)
+
+    def split(A, dtype):
+        s = 2.0 ** (13 - np.floor(np.log2(np.abs(A).max(0)))) if dtype == torch.float16 else np.ones(A.shape[1])
+        t = torch.from_numpy(A * s)
+        hi = t.to(dtype).double()
+        lo = (t - hi).to(dtype).double()
+        return hi.numpy(), lo.numpy(), s
+
+    errs = {}
+    for dtype in (torch.float16, torch.bfloat16):
+        Xh, Xl, sx = split(X, dtype)
+        Bh, Bl, sb = split(B, dtype)
+        P = (Bh.T @ Xh + Bh.T @ Xl + Bl.T @ Xh) / sb[:, None] / sx[None, :]
+        Q = (Xh.T @ Xh + Xh.T @ Xl + Xl.T @ Xh) / sx[:, None] / sx[None, :]
+        errs[dtype] = np.abs(corr_from(P, Q) - want)[off].max()
+    assert errs[torch.float16] < 5e-8, errs                                                      # (2)
+    assert errs[torch.bfloat16] > 2e-7, errs
