@@ -273,3 +273,34 @@ def test_exponential_clock_sampling_is_numpy_choice_without_replacement():
     want = p[:, None] * p[None, :] / (1 - p[:, None])
     np.fill_diagonal(want, 0.0)
     assert np.abs(p1 - want).max() < tol
+
+
+def test_feistel_cycle_walk_is_a_bijection():
+    """The permutation behind the device randomised control (k_permute_rows_nsign, csrc/random.cu), restated in NumPy:
+    a 4-round Feistel network on 2h bits, cycle-walked into [0, C), is a bijection of the cells for every gene key."""
+    def mix32(x):
+        x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
+        x ^= x >> 16; x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+        x ^= x >> 13; x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+        x ^= x >> 16
+        return x
+
+    for C in (1, 2, 3, 72, 1000, 4097):
+        h = 1
+        while (1 << (2 * h)) < C:
+            h += 1
+        mask = (1 << h) - 1
+        for g in (0, 1, 12345):
+            kg = (mix32(np.uint64(g) ^ np.uint64(0x1234ABCD)) + 0x9E37) & 0xFFFFFFFF
+            x = np.arange(C, dtype=np.uint64)
+            todo = np.ones(C, dtype=bool)
+            first = True
+            while todo.any():
+                L, R = x[todo] >> h, x[todo] & mask
+                for r in range(4):
+                    f = mix32((R + kg * (2 * r + 1) + 0x9E3779B9 * (r + 1)) & 0xFFFFFFFF) & mask
+                    L, R = R, L ^ f
+                x[todo] = (L << h) | R
+                todo = x >= C if first else todo & (x >= C)
+                first = False
+            assert np.array_equal(np.sort(x), np.arange(C, dtype=np.uint64)), (C, g)
