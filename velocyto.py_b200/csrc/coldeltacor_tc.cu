@@ -17,10 +17,10 @@
 //     eight epilogue warps drain them (tcgen05.ld) into fp32 running sums in registers (round-to-nearest adds)
 //     while the MMAs of the next block run into the other TMEM buffer.
 //
-// One CTA = one 128 cells x 128 targets tile of pairs; warp 0 = TMA producer (six 128 x 64 bf16 operand tiles per
-// gene block, SWIZZLE_128B boxes), warp 1 = MMA issuer (one thread, 24 MMAs 128x128x16 per gene block, accumulators
-// P and Q in TMEM, two buffers = all 512 columns), warps 2..9 = drain + final epilogue.  CTAs are rasterised in
-// groups of 16 cell blocks so that the ~148 tiles in flight share their operand rows through L2.
+// Two kernels: k_coldeltacor_tc (one CTA per 128 x 128 tile, both accumulators in one CTA; kept for A/B runs) and the
+// shipped k_coldeltacor_tc2 (CTA pairs, tcgen05.mma.cta_group::2, further down).  Common structure: warp 0 = TMA
+// producer (128 x 64 fp16 operand tiles, SWIZZLE_128B boxes), warp 1 = MMA issuer (one thread), warps 2..9 = drain +
+// final epilogue; tiles rasterised in groups of 16 cell blocks so the tiles in flight share operand rows through L2.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
