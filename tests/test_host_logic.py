@@ -304,3 +304,27 @@ def test_feistel_cycle_walk_is_a_bijection():
                 todo = x >= C if first else todo & (x >= C)
                 first = False
             assert np.array_equal(np.sort(x), np.arange(C, dtype=np.uint64)), (C, g)
+
+
+def test_normalize_dispatch_matches_reference_interface(monkeypatch):
+    """VelocytoLoom.normalize routes `which` to the four internal normalisers with the reference's keyword mapping
+    (analysis.py:635-676): (S, U) for "both", (Sx, Ux) for "imputed", target_size[0] / [1], use_S_size_for_U ->
+    use_S_size / use_Sx_size; anything else does nothing.  No GPU: the normalisers are replaced by recorders."""
+    from velocyto_b200.analysis import VelocytoLoom
+    calls = []
+    for n in ("S", "U", "Sx", "Ux"):
+        monkeypatch.setattr(VelocytoLoom, "_normalize_" + n,
+                            lambda self, _n=n, **kw: calls.append((_n, kw)), raising=True)
+    vlm = VelocytoLoom.__new__(VelocytoLoom)
+    rel = np.arange(3.0)
+    expect = {"both": ["S", "U"], "S": ["S"], "U": ["U"], "imputed": ["Sx", "Ux"], "Sx": ["Sx"], "Ux": ["Ux"], "bogus": []}
+    for which, names in expect.items():
+        calls.clear()
+        vlm.normalize(which, size=False, log=True, pcount=0.5, relative_size=rel, use_S_size_for_U=True, target_size=(7.0, 9.0))
+        assert [c[0] for c in calls] == names, which
+        for n, kw in calls:
+            assert kw["size"] is False and kw["log"] is True and kw["pcount"] == 0.5 and kw["relative_size"] is rel
+            assert kw["target_size"] == (7.0 if n in ("S", "Sx") else 9.0)
+            assert ("use_S_size" in kw) == (n == "U") and ("use_Sx_size" in kw) == (n == "Ux")
+            if n in ("U", "Ux"):
+                assert kw["use_S_size" if n == "U" else "use_Sx_size"] is True

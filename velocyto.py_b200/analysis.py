@@ -234,24 +234,14 @@ class VelocytoLoom:
                   target_size: Tuple[float, float] = (None, None)) -> None:
         """Normalization interface (analysis.py:635-676): creates ``S_sz``/``S_norm``, ``U_sz``/``U_norm`` or the
         ``Sx``/``Ux`` twins; the matrices stay on the device."""
-        if which == "both":
-            self._normalize_S(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
-            self._normalize_U(size=size, log=log, pcount=pcount, use_S_size=use_S_size_for_U,
-                              relative_size=relative_size, target_size=target_size[1])
-        if "S" == which:
-            self._normalize_S(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
-        if "U" == which:
-            self._normalize_U(size=size, log=log, pcount=pcount, use_S_size=use_S_size_for_U,
-                              relative_size=relative_size, target_size=target_size[1])
-        if which == "imputed":
-            self._normalize_Sx(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
-            self._normalize_Ux(size=size, log=log, pcount=pcount, use_Sx_size=use_S_size_for_U,
-                               relative_size=relative_size, target_size=target_size[1])
-        if "Sx" == which:
-            self._normalize_Sx(size=size, log=log, pcount=pcount, relative_size=relative_size, target_size=target_size[0])
-        if "Ux" == which:
-            self._normalize_Ux(size=size, log=log, pcount=pcount, use_Sx_size=use_S_size_for_U,
-                               relative_size=relative_size, target_size=target_size[1])
+        plan = {"both": ("S", "U"), "S": ("S",), "U": ("U",), "imputed": ("Sx", "Ux"), "Sx": ("Sx",), "Ux": ("Ux",)}
+        for name in plan.get(which, ()):                      # an unknown `which` is a silent no-op in the reference too
+            common = dict(size=size, log=log, pcount=pcount, relative_size=relative_size)
+            if name in ("S", "Sx"):                           # spliced: first entry of target_size
+                getattr(self, "_normalize_" + name)(target_size=target_size[0], **common)
+            else:                                             # unspliced: may borrow the spliced cell sizes
+                borrow = {"use_S_size" if name == "U" else "use_Sx_size": use_S_size_for_U}
+                getattr(self, "_normalize_" + name)(target_size=target_size[1], **borrow, **common)
 
     # ------------------------------------------------------------------ knn_imputation (analysis.py:933-1023)
     def knn_imputation(self, k: int = None, pca_space: float = True, metric: str = "euclidean", diag: float = 1,
