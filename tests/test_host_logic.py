@@ -328,3 +328,25 @@ def test_normalize_dispatch_matches_reference_interface(monkeypatch):
             assert ("use_S_size" in kw) == (n == "U") and ("use_Sx_size" in kw) == (n == "Ux")
             if n in ("U", "Ux"):
                 assert kw["use_S_size" if n == "U" else "use_Sx_size"] is True
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) prints ONE JSON line with the contract's
+    keys; runs the reference's compiled kernel (oracle/_ref) or the oracle port on a tiny bounded sample."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-seconds", "0.5", "--genes", "2000", "--neighbors", "300"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "cells/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["gpu_launches"] == 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert key in line, key
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
