@@ -103,6 +103,29 @@ int velo_transition_prob_partial(int transform, const void *e, const void *d, in
                                  const int64_t *ixs, float *out,
                                  int64_t rows, int64_t cols, int64_t nrndm, double psc, double sigma);
 
+/* ---- cell-sharded host tier (one process per GPU) ----
+ * The reference parallelises colDeltaCor*partial with an OpenMP prange over cells inside one process
+ * (speedboosted.pyx:22-23); at box scale every rank owns a contiguous block of cells [c0, c0 + nc).
+ *
+ * velo_upload_cellmajor: host gene-major block -- `rows` rows of nc values, row pitch src_cols values (a column
+ * block of the reference's rows x cols matrix) -- to nc cell-major fp32 DEVICE rows dst_cm (row stride ld), in
+ * gene-row chunks through PCIe with the transpose/convert on the device.  Pageable host memory is staged through
+ * the library's pinned ring by several host threads.  dst_lo_cm != NULL also writes the fp32 residuals of fp64 data
+ * and sets *lo_nonzero (host int) to 1 when any is non-zero (then the call synchronises `stream`). */
+int velo_upload_cellmajor(const void *src_gc, int elem_bytes, int64_t rows, int64_t nc, int64_t src_cols,
+                          float *dst_cm, float *dst_lo_cm, int *lo_nonzero, int64_t ld, velo_stream_t stream);
+/* velo_transition_prob_partial for the local cells of one rank, once the expression rows of ALL cells are resident on
+ * this GPU (e_all_cm: cols x ld cell-major fp32 DEVICE matrix -- the all-gathered blocks; e_lo_all_cm: its residual
+ * matrix or NULL).  Work already queued on e_ready_stream (the all-gather) is waited for on the device, so the
+ * upload of the first velocity chunk overlaps it.  d_block: HOST gene-major, `rows` rows of nc values at a row pitch
+ * of d_cols values; ixs_block / out_block: HOST nc x nrndm (GLOBAL neighbour ids / P(c -> ixs[c, n]), or the
+ * correlations when sigma <= 0).  d, ixs and out move in cell chunks underneath the correlation kernel. */
+int velo_transition_prob_partial_sharded(int transform, const float *e_all_cm, const float *e_lo_all_cm, int64_t ld,
+                                         velo_stream_t e_ready_stream, const void *d_block, int elem_bytes,
+                                         int64_t d_cols, const int64_t *ixs_block, float *out_block,
+                                         int64_t rows, int64_t cols, int64_t c0, int64_t nc, int64_t nrndm,
+                                         double psc, double sigma);
+
 /* ---------------------------------------------------- (2) device tier ------ */
 /* gene-major (G x C, row-major, host layout of the reference) -> cell-major fp32
  * dst[c * ld + g], c in [0,C), g in [g_off, g_off+G); pad columns are NOT touched.
@@ -154,7 +177,7 @@ int velo_dev_coldeltacor_ex(int transform, int rule,
 
 /* K2g: the all-pairs LINEAR variant (x_colDeltaCor, speedboosted.pyx:13-87; `_colDeltaCor` :542-550) on the tensor
  * cores: out[r * out_ld + i] = pearson_g(e[i, g] - e[c0 + r, g], d[r, g]) for every target i in [0, C), from the two
- * products P = B X^T and Q = X X^T over the gene axis (bf16 hi/lo split operands, tcgen05.mma, fp32 block sums drained
+ * products P = B X^T and Q = X X^T over the gene axis (fp16 hi/lo split operands -- bf16 pairs are 6 bits short, DESIGN.md -- tcgen05.mma, fp32 block sums drained
  * from TMEM every 64 genes; DESIGN.md "K2g").  Self pairs and coincident cells give NaN like the reference.
  * Scratch (velo_coldeltacor_tc_workspace_bytes) comes from the stream-ordered pool.  dbgP/dbgQ: optional nc x out_ld
  * raw products for diagnostics (both NULL in production). */
@@ -179,6 +202,13 @@ int velo_dev_scatter_dense(const float *out, int64_t out_ld, const int32_t *ixs,
 int velo_dev_transition_prob(const float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld,
                              float *p, int64_t p_ld, int64_t c0, int64_t nc, int64_t m,
                              double sigma, velo_stream_t stream);
+/* As above with the NaN rule selectable: patch_nan != 0 is the knn_random branch (NaN -> 1, analysis.py:1605-1606);
+ * patch_nan == 0 is the "full" branch (analysis.py:1666-1668 only zeroes the diagonal): a NaN correlation makes its
+ * whole row of probabilities NaN, as exp(NaN) and the NaN row sum do in the reference.  The row maximum is
+ * subtracted before exponentiating, so any sigma > 0 is safe in fp32. */
+int velo_dev_transition_prob_ex(const float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld,
+                                float *p, int64_t p_ld, int64_t c0, int64_t nc, int64_t m,
+                                double sigma, int patch_nan, velo_stream_t stream);
 
 /* ---- gamma fits (K4): replaces the per-gene SciPy loop of velocyto/estimation.py:173-366 ----
  * S_cm = X (spliced, independent), U_cm = Y (unspliced, dependent), W_cm weights; all C x ld(w)

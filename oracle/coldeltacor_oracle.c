@@ -134,6 +134,84 @@ int velo_oracle_coldeltacor(const double *e, const double *d, double *rm,
     return failed;
 }
 
+/*
+ * The same arithmetic for a FEW selected cells of a large problem (the bench-shape spot checks: 30 000 genes,
+ * 3 000 neighbours, a handful of cells) -- identical per-pair operation order (pyx:275-336), compact output, and
+ * the thread loop over the (cell, neighbour) PAIRS instead of over cells.
+ *
+ * e        : rows x cols, row-major (the cells involved and all their neighbours, gathered by the caller)
+ * d_sel    : rows x ncells, row-major -- velocity columns of the selected cells only
+ * cells    : ncells column ids (into e) of the selected cells
+ * ixs_sel  : ncells x nrndm neighbour column ids (into e)
+ * out      : ncells x nrndm, out[k*nrndm + n] = corr(cells[k], ixs_sel[k, n])   (assigned, not accumulated)
+ * partial  : zero rule of the partial (1) or full (0) loops
+ * Pinned against velo_oracle_coldeltacor in tests/test_oracle_pinning.py.
+ */
+int velo_oracle_coldeltacor_cells(const double *e, const double *d_sel, double *out,
+                                  const int64_t *ixs_sel, const int64_t *cells, int64_t rows,
+                                  int64_t cols, int64_t ncells, int64_t nrndm, int transform,
+                                  int partial, int num_threads, double psc)
+{
+    int failed = 0;
+    double *ball = (double *)malloc((size_t)rows * (size_t)ncells * sizeof(double));
+    double *ssb = (double *)malloc((size_t)ncells * sizeof(double));
+    if (!ball || !ssb) {
+        free(ball);
+        free(ssb);
+        return 1;
+    }
+    for (int64_t k = 0; k < ncells; ++k) {          /* pyx:300-309, 323-329 */
+        double mub = 0.0, q = 0.0;
+        for (int64_t g = 0; g < rows; ++g) mub += d_sel[g * ncells + k];
+        mub /= (double)rows;
+        for (int64_t g = 0; g < rows; ++g) {
+            const double b = d_sel[g * ncells + k] - mub;
+            ball[k * rows + g] = b;
+            q += b * b;
+        }
+        ssb[k] = 1.0 / sqrt(q);
+    }
+#ifdef _OPENMP
+    if (num_threads < 1) num_threads = 1;
+#pragma omp parallel num_threads(num_threads)
+#endif
+    {
+        double *col = (double *)malloc((size_t)rows * sizeof(double));
+        if (!col) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            failed = 1;
+        } else {
+            int64_t t;
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+            for (t = 0; t < ncells * nrndm; ++t) {
+                const int64_t k = t / nrndm, c = cells[k], i = ixs_sel[t];
+                const double *b = ball + k * rows;
+                double mu = 0.0, ss = 0.0, acc = 0.0;
+                for (int64_t g = 0; g < rows; ++g) {
+                    col[g] = vo_transform(e[g * cols + i] - e[g * cols + c], transform, partial, psc);
+                    mu += col[g];
+                }
+                mu /= (double)rows;
+                for (int64_t g = 0; g < rows; ++g) {
+                    col[g] -= mu;
+                    ss += col[g] * col[g];
+                }
+                ss = 1.0 / sqrt(ss);
+                for (int64_t g = 0; g < rows; ++g) acc += (col[g] * ss) * (b[g] * ssb[k]);
+                out[t] = acc;
+            }
+        }
+        free(col);
+    }
+    free(ball);
+    free(ssb);
+    return failed;
+}
+
 int velo_oracle_max_threads(void)
 {
 #ifdef _OPENMP

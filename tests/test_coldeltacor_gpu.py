@@ -425,3 +425,171 @@ def test_host_tier_pipelined_chunks_match_single_pass(oracle, monkeypatch):
     bad[C - 3, 5] = C + 7
     with pytest.raises((_cabi.VeloError, ValueError)):
         est.colDeltaCorSqrtpartial(e, d, bad, psc=1.0, compact=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# round 2: direct parity at the benchmark shape, the tie-resolving variant at scale, the staged / sharded host tier
+
+def _gather_subproblem(e_cm, lo, d_cm, ix, cells, G):
+    """Selected cells + all their neighbours as a small fp64 problem for ``oracle.coldeltacor_cells``."""
+    import torch
+    cols, sub_ix, pos = [], [], 0
+    for c in cells:
+        nb = ix[c].to(torch.int64)
+        cols.append(torch.cat([torch.tensor([c], device=nb.device), nb]))
+        sub_ix.append(np.arange(pos + 1, pos + 1 + nb.numel()))
+        pos += 1 + nb.numel()
+    cols = torch.cat(cols)
+    e_sub = e_cm.t[cols, :G].to(torch.float64)
+    if lo is not None:
+        e_sub = e_sub + lo[cols, :G].to(torch.float64)             # the fp64 values the reference would be given
+    sel = np.array([s[0] - 1 for s in sub_ix])
+    d_sel = torch.stack([d_cm.t[c, :G] for c in cells], 1).to(torch.float64).cpu().numpy()
+    return np.ascontiguousarray(e_sub.cpu().numpy().T), d_sel, sel, np.stack(sub_ix)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_bench_shape_rows_match_oracle(oracle, exact):
+    """BASELINE config 4 exactly as bench.py runs it -- 100k cells x 30k genes, m = 3000 neighbours, sqrt, psc = 1 (two
+    gene slabs, the in-kernel sort, 3000 accumulators) -- for a handful of cells: correlations within 5e-7 and
+    transition probabilities within 1e-5 of the oracle.  ``exact``: the expression matrix is genuinely fp64 (quantised
+    fp32 values + non-zero fp32 residuals, so fp32 ties between different cells are COMMON) and the tie-resolving
+    kernel variant k_coldeltacor<.,.,EXACT> runs at full scale."""
+    import torch
+    from velocyto_b200 import device as dev
+    free, _ = torch.cuda.mem_get_info()
+    C, G, m = (100_000, 30_000, 3_000) if free > 60e9 else (20_000, 8_000, 3_000)
+    psc, sigma = 1.0, 0.05
+    gen = torch.Generator(device="cuda").manual_seed(5 + exact)
+    e_cm, d_cm = dev.CellMajor.empty(C, G), dev.CellMajor.empty(C, G)
+    if exact:
+        e_cm.lo = torch.zeros_like(e_cm.t)
+    blk = 10_000
+    for c0 in range(0, C, blk):
+        n = min(blk, C - c0)
+        u = torch.rand((n, G), device="cuda", generator=gen)
+        v = -torch.log(torch.rand_like(u).clamp_min(1e-7)) - torch.log(u.clamp_min(1e-7))      # Gamma(2,1)
+        v[torch.rand_like(u) < 0.3] = 0
+        if exact:
+            v = torch.round(v * 4) / 4                                # coarse grid: ties between cells everywhere
+            lo = (torch.rand((n, G), device="cuda", generator=gen) - 0.5) * 2.0 ** -27 * v     # |lo| < half an ulp of v
+            e_cm.lo[c0:c0 + n, :G] = lo
+        e_cm.t[c0:c0 + n, :G] = v
+        z = torch.randn((n, G), device="cuda", generator=gen)
+        d_cm.t[c0:c0 + n, :G] = torch.sign(z) * torch.sqrt(z.abs() + psc)
+    cells = [11, C // 2, C - 1]
+    ix = ((torch.arange(C, device="cuda")[:, None] + 1 +
+           torch.randint(0, C - 1, (C, m), device="cuda", generator=gen)) % C).to(torch.int32)
+    rows = torch.tensor(cells, device="cuda")
+    got = torch.cat([dev.coldeltacor(e_cm, d_cm.rows(c, 1), ix[c:c + 1].contiguous(), "sqrt", psc, c0=c) for c in cells])
+    tp = dev.transition_prob(got.clone(), ix[rows].contiguous(), sigma, c0=C + 5).cpu().numpy()   # c0 past the end: no row is "self"
+    e_sub, d_sel, sel, sub_ix = _gather_subproblem(e_cm, e_cm.lo, d_cm, ix, cells, G)
+    want = oracle.coldeltacor_cells(e_sub, d_sel, sel, sub_ix, "sqrt", psc)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=5e-7)
+    np.testing.assert_allclose(tp, oracle.transition_prob_compact(want, None, sigma), rtol=1e-5, atol=0)
+    if exact:
+        # the residuals matter: dropping them (what fp32 storage alone would see) moves the correlations far past the bar
+        plain = dev.CellMajor(e_cm.t, G)
+        off = dev.coldeltacor(plain, d_cm.rows(cells[0], 1), ix[cells[0]:cells[0] + 1].contiguous(), "sqrt", psc, c0=cells[0])
+        assert float((off - got[:1]).abs().max()) > 1e-4
+
+
+def _host_problem(G, C, m, seed):
+    e, d = synth(G, C, seed, "sqrt", 1.0, fp32_exact=False)          # raw float64: the EXACT path with residuals
+    return e, d, rand_ixs(C, m, seed + 1)
+
+
+def test_host_tier_pageable_equals_pinned(oracle, monkeypatch):
+    """NumPy (pageable) buffers go through the library's pinned staging ring with several host threads; page-locked
+    buffers are copied directly.  Same bits either way, single- and multi-chunk, and both match the oracle."""
+    import torch
+    from velocyto_b200 import _cabi
+    G, C, m, psc, sigma = 1100, 640, 48, 1.0, 0.05
+    e, d, ixs = _host_problem(G, C, m, 41)
+    want_c = oracle.coldeltacor(e, d, ixs, "sqrt", psc)[np.arange(C)[:, None], ixs]
+    want = oracle.transition_prob_compact(want_c, None, sigma)
+    res = {}
+    for chunk in (None, "96"):
+        if chunk is None:
+            monkeypatch.delenv("VELO_HOST_CHUNK_CELLS", raising=False)
+        else:
+            monkeypatch.setenv("VELO_HOST_CHUNK_CELLS", chunk)
+        for kind in ("pageable", "pinned"):
+            if kind == "pinned":
+                bufs = [torch.from_numpy(a).pin_memory() for a in (e, d, ixs)]
+                out = torch.empty((C, m), dtype=torch.float32).pin_memory()
+            else:
+                bufs = [torch.from_numpy(a) for a in (e, d, ixs)]
+                out = torch.empty((C, m), dtype=torch.float32)
+            _cabi.call("velo_transition_prob_partial", _cabi.SQRT, bufs[0].data_ptr(), bufs[1].data_ptr(), 8,
+                       bufs[2].data_ptr(), out.data_ptr(), G, C, m, psc, sigma)
+            res[(chunk, kind)] = out.numpy().copy()
+    first = res[(None, "pageable")]
+    for k, v in res.items():
+        assert np.array_equal(first, v), k
+    np.testing.assert_allclose(first, want, rtol=1e-5, atol=0)
+
+
+def test_sharded_host_entry_matches_single_call(oracle, monkeypatch):
+    """The cell-sharded host tier on ONE GPU playing both ranks of a 2-way split: velo_upload_cellmajor of each block
+    into its slot (column blocks of the full host matrix, passed as strided views), then
+    velo_transition_prob_partial_sharded per block == the single-GPU host call, bit for bit."""
+    import ctypes
+    import torch
+    from velocyto_b200 import _cabi, device as dev
+    from velocyto_b200.sharding import partition, block_size, _host_ptr
+    G, C, m, psc, sigma = 900, 501, 37, 1.0, 0.05
+    e, d, ixs = _host_problem(G, C, m, 43)
+    whole = np.empty((C, m), dtype=np.float32)
+    _cabi.call("velo_transition_prob_partial", _cabi.SQRT, e.ctypes.data, d.ctypes.data, 8, ixs.ctypes.data,
+               whole.ctypes.data, G, C, m, psc, sigma)
+    world, ld = 2, dev.padded_ld(G)
+    b = block_size(C, world)
+    e_full = torch.zeros((world * b, ld), dtype=torch.float32, device="cuda")
+    lo_full = torch.zeros_like(e_full)
+    stream = torch.cuda.current_stream().cuda_stream
+    nz_any = 0
+    for r, (c0, nc) in enumerate(partition(C, world)):
+        ptr, pitch, esz = _host_ptr(e[:, c0:c0 + nc])                 # a view: row pitch = C values
+        assert pitch == C and esz == 8
+        nz = ctypes.c_int(0)
+        _cabi.call("velo_upload_cellmajor", ptr, 8, G, nc, pitch, e_full[r * b:].data_ptr(), lo_full[r * b:].data_ptr(),
+                   ctypes.addressof(nz), ld, stream)
+        nz_any |= nz.value
+    assert nz_any == 1                                                # raw float64 data: residuals present
+    monkeypatch.setenv("VELO_HOST_CHUNK_CELLS", "64")
+    for r, (c0, nc) in enumerate(partition(C, world)):
+        out = np.empty((nc, m), dtype=np.float32)
+        dptr, dpitch, _ = _host_ptr(d[:, c0:c0 + nc])
+        _cabi.call("velo_transition_prob_partial_sharded", _cabi.SQRT, e_full.data_ptr(), lo_full.data_ptr(), ld, stream,
+                   dptr, 8, dpitch, ixs[c0:c0 + nc].ctypes.data, out.ctypes.data, G, C, c0, nc, m, psc, sigma)
+        assert np.array_equal(out, whole[c0:c0 + nc]), f"block {r}"
+    # the Python front (world size 1: no process group) drives the same two entry points
+    from velocyto_b200.sharding import CellShardedHostTransitionProb
+    out1 = np.empty((C, m), dtype=np.float32)
+    CellShardedHostTransitionProb(G, C, "sqrt", psc, sigma).run(e, d, ixs, out1)
+    assert np.array_equal(out1, whole)
+
+
+def test_transition_prob_small_sigma_and_nan_rules():
+    """Row-max subtraction: sigma_corr far below the fp32 overflow point of exp(corr / sigma) (0.0113) still gives the
+    fp64 result; NaN -> 1 only when asked (knn_random branch), otherwise the row is NaN (full branch)."""
+    import torch
+    from velocyto_b200 import device as dev
+    rng = np.random.default_rng(3)
+    nc, m = 64, 200
+    corr = rng.uniform(-1, 1, (nc, m)).astype(np.float32)
+    corr[5, 7] = np.nan
+    ix = np.stack([(c + 1 + rng.choice(300 - 1, m, replace=False)) % 300 for c in range(nc)])
+    ix[9, 3] = 9                                                       # a self pair -> 0
+    for sigma in (0.05, 0.004):
+        c64 = corr.astype(np.float64)
+        c64[9, 3] = 0
+        c64[np.isnan(c64)] = 1
+        w = np.exp((c64 - c64.max(1, keepdims=True)) / sigma)
+        want = w / w.sum(1, keepdims=True)
+        got = dev.transition_prob(torch.from_numpy(corr).cuda(), dev.indices_to_device(ix, 300), sigma).cpu().numpy()
+        assert np.isfinite(got).all()
+        np.testing.assert_allclose(got, want, rtol=5e-5 if sigma < 0.01 else 2e-6, atol=1e-30)
+    got = dev.transition_prob(torch.from_numpy(corr).cuda(), dev.indices_to_device(ix, 300), 0.05, patch_nan=False).cpu().numpy()
+    assert np.isnan(got[5]).all() and np.isfinite(np.delete(got, 5, 0)).all()

@@ -350,3 +350,40 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_balanced_knn_routes_unserved_metrics_to_scikit_learn():
+    """The device search serves Euclidean / correlation / cosine; any other scikit-learn metric must go to
+    scikit-learn with THAT metric (the reference passes it through, neighbors.py:239-243) -- never silently to the
+    Euclidean kernel.  Runs without a GPU because the manhattan search never touches the device."""
+    from sklearn.neighbors import NearestNeighbors
+    from velocyto_b200.neighbors import BalancedKNN
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(120, 6))
+    bk = BalancedKNN(k=5, sight_k=20, maxl=10, metric="manhattan")
+    assert bk._device_metric() is None
+    bk.fit(X)
+    dist, idx, _ = bk.kneighbors()
+    d_ref, i_ref = NearestNeighbors(n_neighbors=21, metric="manhattan").fit(X).kneighbors(X)
+    assert np.array_equal(bk.dsi, i_ref) and np.allclose(bk.dist, d_ref)
+    d_euc, i_euc = NearestNeighbors(n_neighbors=21).fit(X).kneighbors(X)
+    assert not np.array_equal(bk.dsi, i_euc)                            # and it is NOT the Euclidean answer
+    assert BalancedKNN(metric="euclidean")._device_metric() == "euclidean"
+    assert BalancedKNN(metric="correlation")._device_metric() == "correlation"
+    assert BalancedKNN(metric="euclidean", search="host")._device_metric() is None
+
+
+def test_sharded_host_front_helpers():
+    from velocyto_b200.sharding import _host_ptr, needs_residuals
+    a = np.zeros((7, 40))
+    ptr, pitch, esz = _host_ptr(a[:, 8:20])                             # a cell block of the gene-major matrix: no copy
+    assert ptr == a.ctypes.data + 8 * 8 and pitch == 40 and esz == 8
+    import torch
+    t = torch.zeros((5, 12), dtype=torch.float32)
+    assert _host_ptr(t) == (t.data_ptr(), 12, 4)
+    with pytest.raises(AssertionError):
+        _host_ptr(a.T)                                                  # genes must stay the slow axis
+    # same rule as the one-GPU host tier (capi.cu): residuals only for fp64 data under a transform that jumps at 0
+    assert needs_residuals("sqrt", 1.0, 8) and not needs_residuals("sqrt", 1e-10, 8)
+    assert not needs_residuals("sqrt", 1.0, 4) and not needs_residuals("linear", 0.0, 8)
+    assert needs_residuals("log10", 0.5, 8) and not needs_residuals("log10", 1.0, 8)

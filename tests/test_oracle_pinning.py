@@ -51,6 +51,29 @@ def test_coldeltacor_oracle_matches_golden(oracle, golden, name, psc):
 
 
 @pytest.mark.parametrize("name,psc", CASES)
+def test_selected_cells_oracle_matches_golden(oracle, golden, name, psc):
+    """``coldeltacor_cells`` (the few-cells entry used for the bench-shape spot checks) against the reference's golden
+    vectors, both zero rules: it must be the same arithmetic as the whole-problem oracle pinned above."""
+    g = golden("coldeltacor_small.npz")
+    e, ixs = g["e"], g["ixs"].astype(np.int64)
+    d = _d(g["z"], name, psc)
+    tag = f"{name}_{psc:g}"
+    C = e.shape[1]
+    cells = np.array([0, 3, C // 2, C - 1])
+    ok = ~_degenerate_pairs(e)
+    part = oracle.coldeltacor_cells(e, d[:, cells], cells, ixs[cells], name, psc, partial=True, threads=2)
+    want = g[f"partial_{tag}"][cells[:, None], ixs[cells]]
+    sel = ok[cells[:, None], ixs[cells]]
+    np.testing.assert_allclose(part[sel], want[sel], rtol=0, atol=2e-12)
+    everyone = np.tile(np.arange(C), (cells.size, 1))
+    full = oracle.coldeltacor_cells(e, d[:, cells], cells, everyone, name, psc, partial=False, threads=2)
+    np.testing.assert_allclose(full[ok[cells]], g[f"full_{tag}"][cells][ok[cells]], rtol=0, atol=2e-12)
+    # and bit-for-bit the whole-problem oracle (same operation order per pair)
+    whole = oracle.coldeltacor(e, d, ixs, name, psc, threads=2)[cells[:, None], ixs[cells]]
+    assert np.array_equal(part, whole, equal_nan=True)
+
+
+@pytest.mark.parametrize("name,psc", CASES)
 def test_coldeltacor_oracle_matches_live_reference(oracle, name, psc):
     if oracle.load_ref_speedboosted() is None:
         pytest.skip("oracle/_ref not built")

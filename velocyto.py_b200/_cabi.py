@@ -39,6 +39,9 @@ PROTOTYPES = {
     "velo_colDeltaCorLog10partial": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _dbl]),
     "velo_colDeltaCorpartial_compact": (_int, [_int, _ptr, _ptr, _int, _ptr, _ptr, _i64, _i64, _i64, _dbl]),
     "velo_transition_prob_partial": (_int, [_int, _ptr, _ptr, _int, _ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl]),
+    "velo_upload_cellmajor": (_int, [_ptr, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "velo_transition_prob_partial_sharded": (_int, [_int, _ptr, _ptr, _i64, _ptr, _ptr, _int, _i64, _ptr, _ptr,
+                                                    _i64, _i64, _i64, _i64, _i64, _dbl, _dbl]),
     # device tier
     "velo_dev_pack_cellmajor": (_int, [_ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr]),
     "velo_dev_pack_cellmajor_split": (_int, [_ptr, _int, _i64, _i64, _ptr, _ptr, _ptr, _i64, _i64, _ptr]),
@@ -55,6 +58,7 @@ PROTOTYPES = {
     "velo_get_tensor_cores": (_int, []),
     "velo_dev_scatter_dense": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr]),
     "velo_dev_transition_prob": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _dbl, _ptr]),
+    "velo_dev_transition_prob_ex": (_int, [_ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _dbl, _int, _ptr]),
     "velo_dev_fit_gammas": (_int, [_int, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _dbl, _dbl,
                                    _ptr, _ptr, _ptr, _ptr, _ptr]),
     "velo_dev_fit_gammas_ex": (_int, [_int, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _dbl, _dbl, _ptr, _ptr,

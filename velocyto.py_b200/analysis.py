@@ -51,8 +51,13 @@ class _DeviceBacked:
             return host[self.name]
         devs = obj.__dict__.setdefault("_devs", {})
         if self.name in devs:
-            host[self.name] = devs[self.name].to_gene_major(np.float64)
-            return host[self.name]
+            # a download of device-born data: handed out READ-ONLY, because the device twin is what the later stages
+            # read -- an in-place edit of this array would silently not reach it.  Assign a new array instead
+            # (``vlm.delta_S = edited``): __set__ drops the device twin and the next stage uploads the new values.
+            arr = devs[self.name].to_gene_major(np.float64)
+            arr.flags.writeable = False
+            host[self.name] = arr
+            return arr
         raise AttributeError(f"'{type(obj).__name__}' object has no attribute '{self.name}'")
 
     def __set__(self, obj, value):
@@ -65,11 +70,12 @@ class _DeviceBacked:
         obj.__dict__.setdefault("_devs", {}).pop(self.name, None)
 
 
-def knn_graph_device(data: np.ndarray, k: int, mode: str = "connectivity", include_self: bool = False) -> sparse.csr_matrix:
-    """Euclidean kNN graph built by the brute-force device kernel (``velo_dev_knn``): the CSR scikit-learn's
+def knn_graph_device(data: np.ndarray, k: int, mode: str = "connectivity", include_self: bool = False,
+                     metric: str = "euclidean") -> sparse.csr_matrix:
+    """kNN graph built by the brute-force device kernel (``velo_dev_knn``): the CSR scikit-learn's
     ``kneighbors_graph(X=None, mode=...)`` returns -- k entries per row in ascending distance."""
     from . import device as dev
-    idx, dist = dev.knn(np.ascontiguousarray(data, dtype=np.float64), k, include_self)
+    idx, dist = dev.knn(np.ascontiguousarray(data, dtype=np.float64), k, include_self, metric)
     n = idx.shape[0]
     vals = dist.cpu().numpy().ravel() if mode == "distance" else np.ones(n * k)
     return sparse.csr_matrix((vals, idx.cpu().numpy().astype(np.int32).ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
@@ -77,11 +83,13 @@ def knn_graph_device(data: np.ndarray, k: int, mode: str = "connectivity", inclu
 
 def knn_distance_matrix(data: np.ndarray, metric: str = None, k: int = 40, mode: str = "connectivity",
                         n_jobs: int = 4) -> sparse.csr_matrix:
-    """k nearest neighbours NOT including the point itself (velocyto/neighbors.py:363-376).  Euclidean searches run on
-    the device (exact, brute force); the correlation metric stays with scikit-learn on the host."""
+    """k nearest neighbours NOT including the point itself (velocyto/neighbors.py:363-376).  The reference passes
+    ``metric`` to scikit-learn only when it is "correlation" (otherwise the default Euclidean search); both run on the
+    device (exact, brute force).  scikit-learn remains only for k or dimensions beyond the kernel's limits."""
     from . import device as dev
-    if metric != "correlation" and k <= dev.KNN_MAX_K and np.shape(data)[1] <= 4096:
-        return knn_graph_device(data, k, mode)
+    dev_metric = "correlation" if metric == "correlation" else "euclidean"
+    if k <= dev.KNN_MAX_K and np.shape(data)[1] <= 4096:
+        return knn_graph_device(data, k, mode, metric=dev_metric)
     from sklearn.neighbors import NearestNeighbors
     if metric == "correlation":
         nn = NearestNeighbors(n_neighbors=k, metric="correlation", algorithm="brute", n_jobs=n_jobs)
@@ -272,7 +280,11 @@ class VelocytoLoom:
                 raise ValueError("group_constraint is currently supported only if the argument balanced is set to True")
             self.knn = knn_distance_matrix(space, metric=metric, k=k, mode="distance", n_jobs=n_jobs)
         connectivity = connectivity_with_diagonal(self.knn, diag)                        # analysis.py:1006-1009
-        self.knn_smoothing_w = connectivity_to_weights(connectivity)                     # analysis.py:1010
+        # connectivity_to_weights (analysis.py:1010, neighbors.py:385-390) on the CSR arrays: rows / rowsum.  SciPy's
+        # `multiply` by a dense column returns COO and costs a second at 5e6 edges; the values are the same.
+        rowsum = np.add.reduceat(connectivity.data, connectivity.indptr[:-1])
+        self.knn_smoothing_w = sparse.csr_matrix((connectivity.data / np.repeat(rowsum, np.diff(connectivity.indptr)),
+                                                  connectivity.indices, connectivity.indptr), shape=connectivity.shape)
         self._smooth(maximum, size_norm)
 
     def knn_imputation_precomputed(self, knn_smoothing_w, maximum: bool = False) -> None:
@@ -281,29 +293,49 @@ class VelocytoLoom:
         self._smooth(maximum, True)
 
     def _smooth(self, maximum: bool, size_norm: bool) -> None:
-        from . import device as dev
-        from .neighbors import _csr_rows
-        indptr, indices, weights, wcsr = _csr_rows(self.knn_smoothing_w)
-        assert np.allclose(np.asarray(wcsr.sum(1)).ravel(), 1), "weight matrix need to sum to one over the columns"
-        src_s, src_u = ("S_sz", "U_sz") if size_norm else ("S", "U")                    # analysis.py:1011-1016
         import torch
+        from . import device as dev
         dv = dev.require_cuda()
-        ip, ix, wt = (torch.from_numpy(indptr).to(dv), torch.from_numpy(indices).to(dv), torch.from_numpy(weights).to(dv))
+        ip, ix, wt = self._weights_to_device(self.knn_smoothing_w, dv)
+        # the reference's `assert np.allclose(w_.sum(0), 1)` (neighbors.py:422), evaluated on the device
+        rows = torch.repeat_interleave(torch.arange(ip.numel() - 1, device=dv), ip[1:] - ip[:-1])
+        rsum = torch.zeros(ip.numel() - 1, dtype=torch.float64, device=dv).index_add_(0, rows, wt.double())
+        assert bool(((rsum - 1).abs() <= 1e-5).all()), "weight matrix need to sum to one over the columns"
+        src_s, src_u = ("S_sz", "U_sz") if size_norm else ("S", "U")                    # analysis.py:1011-1016
         host = self.__dict__.setdefault("_host", {})
 
-        def smooth(name):
+        def smooth(name, own_max):
             # sparse counts (an extension: the reference is dense-only) stay CSR on the device and only the smoothed
             # matrix is dense -- what makes the 500k-cell configuration fit (velo_dev_knn_smooth_csr)
             if name in host and sparse.issparse(host[name]):
-                return dev.knn_smooth_csr(ip, ix, wt, sparse.csr_matrix(host[name].T), maximum=maximum)
-            return dev.knn_smooth(ip, ix, wt, self._dev(name), maximum)
+                return dev.knn_smooth_csr(ip, ix, wt, sparse.csr_matrix(host[name].T), maximum=own_max)
+            return dev.knn_smooth(ip, ix, wt, self._dev(name), own_max)
 
-        Sx, Ux = smooth(src_s), smooth(src_u)
+        # maximum: np.maximum(self.S_sz, self.Sx) -- against the SIZE-NORMALISED counts whatever was smoothed
+        # (analysis.py:1017-1019); fused into the kernel when that is also its input
+        Sx, Ux = smooth(src_s, maximum and size_norm), smooth(src_u, maximum and size_norm)
+        if maximum and not size_norm:
+            torch.maximum(Sx.t, self._dev("S_sz").t, out=Sx.t)
+            torch.maximum(Ux.t, self._dev("U_sz").t, out=Ux.t)
         self._set_dev("Sx", Sx)
         self._set_dev("Ux", Ux)
-        # "a differently named variable for backwards compatibility" -- copies in the reference (analysis.py:1022-1023)
-        self._set_dev("Sx_sz", dev.CellMajor(Sx.t.clone(), Sx.G))
-        self._set_dev("Ux_sz", dev.CellMajor(Ux.t.clone(), Ux.G))
+        # "a differently named variable for backwards compatibility" (analysis.py:1022-1023): copies in the reference;
+        # here the SAME device matrix under both names -- no kernel ever writes a named matrix in place (every stage
+        # allocates its output), and a host-side assignment replaces only the name it targets
+        self._set_dev("Sx_sz", Sx)
+        self._set_dev("Ux_sz", Ux)
+
+    @staticmethod
+    def _weights_to_device(w, dv):
+        """CSR-by-rows arrays of the smoothing weights as device tensors ``(indptr int64, indices int32, data fp32)``.
+        A SciPy CSR matrix with canonical (duplicate-free) rows -- what ``connectivity_to_weights`` returns -- goes
+        over as it is; anything else is canonicalised by SciPy first."""
+        import torch
+        if not isinstance(w, sparse.csr_matrix):
+            w = sparse.csr_matrix(w)                   # COO (what SciPy's multiply returns) / dense: canonicalised by SciPy
+            w.sum_duplicates()
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dv).to(dt)
+        return to(w.indptr, torch.int64), to(w.indices, torch.int32), to(w.data, torch.float32)
 
     # ------------------------------------------------------------------ fit_gammas (analysis.py:1120-1260)
     def fit_gammas(self, steady_state_bool: np.ndarray = None, use_imputed_data: bool = True, use_size_norm: bool = True,
@@ -337,7 +369,14 @@ class VelocytoLoom:
             logging.warning("limit_gamma not implemented with this settings")            # analysis.py:1230,1242,1253
         use_lim = limit_gamma and weighted and not use_fix
         if mask is not None and (use_fix or use_lim):
-            raise NotImplementedError("fixperc_q / limit_gamma with a steady_state cell selection")
+            # the reference slices tmpS[:, steady_state] before every fit (analysis.py:1223-1256), so the percentile
+            # constraints of fixperc_q / limit_gamma (estimation.py:199-204, 221-224) see the selected cells only:
+            # compact the cell rows on the device and fit without a mask
+            sel = torch.from_numpy(np.flatnonzero(mask)).to(Sd.t.device)
+            Sd, Ud = dev.CellMajor(Sd.t.index_select(0, sel), Sd.G), dev.CellMajor(Ud.t.index_select(0, sel), Ud.G)
+            if Wd is not None:
+                Wd = dev.CellMajor(Wd.t.index_select(0, sel), Wd.G)
+            mask_t = None
         qf, up = dev.fit_constraints(Sd, Ud, use_fix, use_lim)
         lo = 1e-8 if (mode == dev.FIT_SLOPE_WEIGHTED_OFFSET or use_lim) else 0.0
         g, q, r2, _ = dev.fit_gammas(mode, Sd, Ud, Wd, mask_t, lo, 20.0, want_r2=weighted and not use_fix,
@@ -409,10 +448,9 @@ class VelocytoLoom:
             out = dev.velocity_chain(self._dev("Sx_sz"), self._dev("Ux_sz"), g, q, assumption=assumption,
                                      dt_shift=delta_t, want=("delta_S",))
         else:
-            nS = self.which_S_for_pred
-            nU = "Ux_sz" if nS == "Sx_sz" else "Ux"
-            out = dev.velocity_chain(self._dev(nS), self._dev(nU), self._pred_gamma, self._pred_q, dt_shift=delta_t,
-                                     eps=getattr(self, "_velocity_eps", None), want=("delta_S",))
+            # delta_S = delta_t * self.velocity (analysis.py:1399): whatever `velocity` currently is -- the device
+            # matrix calculate_velocity left, or an array the user assigned / masked since (re-uploaded by _dev)
+            out = {"delta_S": dev.delta_transform(self._dev("velocity"), delta_t, "linear", 0.0)}
         self._shift = (assumption, float(delta_t))
         self._set_dev("delta_S", out["delta_S"])
 
@@ -599,9 +637,17 @@ class VelocytoLoom:
             names.append(("corrcoef_random", "transition_prob_random"))
         for cname, pname in names:
             corr = getattr(self, "_" + cname + "_dev")
+            poisoned = None
             if ix is None:
+                # "full" branch: exp(corrcoef / sigma) * embedding_knn.A over the DENSE matrix (analysis.py:1697): a NaN
+                # anywhere in a row (only the diagonal was zeroed, :1666-1668) makes exp(NaN) * 0 = NaN and with it
+                # the whole row of transition probabilities, neighbours or not
+                poisoned = torch.isnan(corr).any(dim=1)
                 corr = torch.gather(corr, 1, ix_m.to(torch.int64))
-            tp = dev.transition_prob(corr.contiguous(), ix_m, sigma_corr)
+            # NaN -> 1 belongs to the knn_random branch only (analysis.py:1604-1612)
+            tp = dev.transition_prob(corr.contiguous(), ix_m, sigma_corr, patch_nan=ix is not None)
+            if poisoned is not None and bool(poisoned.any()):
+                tp[poisoned] = float("nan")
             setattr(self, "_" + pname + "_dev", tp)
             setattr(self, pname + "_compact", tp.cpu().numpy())
             if C <= dense_limit:

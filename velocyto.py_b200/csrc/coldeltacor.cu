@@ -473,11 +473,15 @@ __global__ void k_scatter_dense(const float *__restrict__ out, int64_t out_ld, c
     }
 }
 
-// transition probabilities, one warp per cell row
+// transition probabilities, one warp per cell row.  exp((v - vmax)/sigma): the row maximum is subtracted first (it
+// cancels in the normalisation), so small sigma_corr cannot overflow fp32 -- the reference works in fp64 and stays
+// finite down to sigma ~ 0.0014 (analysis.py:1697-1698).  patch_nan: NaN -> 1 as the knn_random branch does
+// (analysis.py:1605-1606); without it a NaN poisons its whole row exactly like exp(NaN) / NaN-sum in the reference's
+// "full" branch (analysis.py:1666-1668 only zeroes the diagonal).
 __global__ void __launch_bounds__(256) k_transition_prob(const float *__restrict__ corr, int64_t ld,
                                                          const int32_t *__restrict__ ixs, int64_t ixs_ld,
                                                          float *__restrict__ p, int64_t p_ld, int64_t c0, int64_t nc,
-                                                         int64_t m, float inv_sigma)
+                                                         int64_t m, float inv_sigma, int patch_nan)
 {
     const int lane = threadIdx.x & 31;
     const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -485,18 +489,33 @@ __global__ void __launch_bounds__(256) k_transition_prob(const float *__restrict
     const float *cr = corr + r * ld;
     float *pr = p + r * p_ld;
     const int64_t self = c0 + r;
-    double sum = 0.0;
+    float vmax = -INFINITY;
+    bool bad = false;
     for (int64_t n = lane; n < m; n += 32) {
         float v = cr[n];
         const int64_t i = ixs ? static_cast<int64_t>(ixs[r * ixs_ld + n]) : n;
         if (i == self) v = 0.0f;            // np.fill_diagonal(corrcoef, 0)     analysis.py:1604
-        else if (v != v) v = 1.0f;          // NaN -> 1                           analysis.py:1605-1606
-        const float ex = expf(v * inv_sigma);
+        else if (v != v) {
+            if (patch_nan) v = 1.0f;        // NaN -> 1                           analysis.py:1605-1606
+            else bad = true;
+        }
+        if (v == v) vmax = fmaxf(vmax, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    bad = __any_sync(0xffffffffu, bad);
+    double sum = 0.0;
+    for (int64_t n = lane; n < m; n += 32) {
+        float v = cr[n];
+        const int64_t i = ixs ? static_cast<int64_t>(ixs[r * ixs_ld + n]) : n;
+        if (i == self) v = 0.0f;
+        else if (v != v) v = 1.0f;
+        const float ex = expf((v - vmax) * inv_sigma);
         pr[n] = ex;
         sum += static_cast<double>(ex);
     }
     sum = warp_sum(sum);
-    const float inv = static_cast<float>(1.0 / sum);
+    const float inv = bad ? __int_as_float(0x7fc00000) : static_cast<float>(1.0 / sum);
     __syncwarp();
     for (int64_t n = lane; n < m; n += 32) pr[n] *= inv;
 }
@@ -626,15 +645,22 @@ extern "C" int velo_dev_scatter_dense(const float *out, int64_t out_ld, const in
     return VELO_OK;
 }
 
-extern "C" int velo_dev_transition_prob(const float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld, float *p,
-                                        int64_t p_ld, int64_t c0, int64_t nc, int64_t m, double sigma,
-                                        velo_stream_t stream)
+extern "C" int velo_dev_transition_prob_ex(const float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld, float *p,
+                                           int64_t p_ld, int64_t c0, int64_t nc, int64_t m, double sigma,
+                                           int patch_nan, velo_stream_t stream)
 {
     VELO_REQUIRE(corr && p && nc >= 0 && m > 0 && ld >= m && p_ld >= m && sigma > 0, "transition_prob: bad arguments");
     if (nc == 0) return VELO_OK;
     const int wpb = 8;
     k_transition_prob<<<static_cast<unsigned>((nc + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(
-        corr, ld, ixs, ixs_ld, p, p_ld, c0, nc, m, static_cast<float>(1.0 / sigma));
+        corr, ld, ixs, ixs_ld, p, p_ld, c0, nc, m, static_cast<float>(1.0 / sigma), patch_nan);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
+}
+
+extern "C" int velo_dev_transition_prob(const float *corr, int64_t ld, const int32_t *ixs, int64_t ixs_ld, float *p,
+                                        int64_t p_ld, int64_t c0, int64_t nc, int64_t m, double sigma,
+                                        velo_stream_t stream)
+{
+    return velo_dev_transition_prob_ex(corr, ld, ixs, ixs_ld, p, p_ld, c0, nc, m, sigma, 1, stream);
 }

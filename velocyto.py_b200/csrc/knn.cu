@@ -26,7 +26,7 @@ struct KnnParams {
     int32_t *out_idx;      // C x k
     double *out_dist;      // C x k or null
     uint32_t *scratch;     // gridDim.x x C
-    int *overflow;         // set to 1 when more than P candidates tie at the threshold
+    int *overflow;         // internal consistency flag of the tie-resolving path (stays 0)
 };
 
 __global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
@@ -108,7 +108,64 @@ __global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
             }
         }
         __syncthreads();
-        if (tid == 0 && n_cand > static_cast<unsigned int>(p.P)) atomicExch(p.overflow, 1);
+        if (n_cand > static_cast<unsigned int>(p.P)) {
+            // More points tie with the k-th distance (same fp32 key) than the candidate buffer has room for: in
+            // practice exact duplicates (identical cells in PCA / embedding space).  Such ties are interchangeable,
+            // so they are resolved by LOWEST INDEX: a second radix select, over the point index among the tied keys,
+            // finds the index bound T below which exactly rem + 1 ties lie (rem = rank of the k-th neighbour inside
+            // the tie group, left over from the key select); the candidate set is then exactly k points.
+            __syncthreads();
+            uint32_t ipre = 0, imask = 0;
+            int64_t irem = rem;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                for (int b = tid; b < 256; b += nt) hist[b] = 0;
+                __syncthreads();
+                for (int64_t j = tid; j < p.C; j += nt)
+                    if (keys[j] == prefix && (static_cast<uint32_t>(j) & imask) == ipre)
+                        atomicAdd(&hist[(static_cast<uint32_t>(j) >> shift) & 255u], 1u);
+                __syncthreads();
+                if (tid == 0) {
+                    int64_t cum = 0;
+                    int b = 0;
+                    for (; b < 255; ++b) {
+                        if (cum + hist[b] > irem) break;
+                        cum += hist[b];
+                    }
+                    sel[0] = static_cast<unsigned long long>(b);
+                    sel[1] = static_cast<unsigned long long>(irem - cum);
+                }
+                __syncthreads();
+                ipre |= static_cast<uint32_t>(sel[0]) << shift;
+                imask |= 255u << shift;
+                irem = static_cast<int64_t>(sel[1]);
+                __syncthreads();
+            }
+            if (tid == 0) n_cand = 0;
+            for (int i = tid; i < p.P; i += nt) {
+                c_key[i] = inf;
+                c_idx[i] = 0x7fffffff;
+            }
+            __syncthreads();
+            for (int64_t j = tid; j < p.C; j += nt) {
+                const uint32_t u = keys[j];
+                if (u < prefix || (u == prefix && static_cast<uint32_t>(j) <= ipre)) {
+                    const unsigned int slot = atomicAdd(&n_cand, 1u);
+                    if (slot < static_cast<unsigned int>(p.P)) {
+                        double d2 = 0.0;
+                        const double *xj = p.X + j * p.D;
+                        for (int d = 0; d < p.D; ++d) {
+                            const double t = xj[d] - xq[d];
+                            d2 = fma(t, t, d2);
+                        }
+                        c_key[slot] = d2;
+                        c_idx[slot] = static_cast<int32_t>(j);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0 && n_cand != static_cast<unsigned int>(p.k)) atomicExch(p.overflow, 1);   // cannot happen
+        }
         // 4. bitonic sort by (distance, index)
         for (int kk = 2; kk <= p.P; kk <<= 1)
             for (int jj = kk >> 1; jj > 0; jj >>= 1) {
@@ -175,6 +232,6 @@ extern "C" int velo_dev_knn(const double *X, int64_t C, int D, int k, int includ
     cudaFreeAsync(scratch, st);
     cudaFreeAsync(overflow, st);
     VELO_CUDA_TRY(e);
-    VELO_REQUIRE(flag == 0, "knn: more than %d points tie with the k-th neighbour distance (duplicated points?)", P - k);
+    VELO_REQUIRE(flag == 0, "knn: internal error in the tie-resolving selection (k = %d)", k);
     return VELO_OK;
 }

@@ -191,14 +191,16 @@ def coldeltacor_linear_tc(e_cm: CellMajor, d_cm: CellMajor, c0: int = 0, stats: 
 
 
 def transition_prob(corr: torch.Tensor, ixs: Optional[torch.Tensor], sigma: float, c0: int = 0,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Compact ``exp(corr/sigma)`` row-normalised with self->0 / NaN->1 patches (analysis.py:1604-1612,1697-1698)."""
+                    out: Optional[torch.Tensor] = None, patch_nan: bool = True) -> torch.Tensor:
+    """Compact ``exp(corr/sigma)`` row-normalised (analysis.py:1697-1698) with the self->0 patch and, with
+    ``patch_nan`` (the knn_random branch, analysis.py:1604-1612), NaN->1; ``patch_nan=False`` is the "full" branch
+    (analysis.py:1666-1668): a NaN correlation turns its whole row NaN, as in the reference."""
     nc, m = corr.shape
     if out is None:
         out = torch.empty_like(corr)
-    _cabi.call("velo_dev_transition_prob", corr.data_ptr(), corr.stride(0), 0 if ixs is None else ixs.data_ptr(),
+    _cabi.call("velo_dev_transition_prob_ex", corr.data_ptr(), corr.stride(0), 0 if ixs is None else ixs.data_ptr(),
                0 if ixs is None else ixs.stride(0), out.data_ptr(), out.stride(0), c0, nc, m, float(sigma),
-               _stream_ptr())
+               int(bool(patch_nan)), _stream_ptr())
     return out
 
 
@@ -426,19 +428,33 @@ def knn_smooth_csr(w_indptr, w_indices, w_weights, S_csr, g0: int = 0, ng: Optio
 
 # --------------------------------------------------------------------------- exact kNN
 KNN_MAX_K = 14000
+# metrics the brute-force kernel serves: Euclidean directly; correlation / cosine through the identity
+# |x^ - y^|^2 = 2 (1 - <x^, y^>) on rows scaled to unit norm (after centring, for correlation) -- the neighbour ORDER
+# under the reference's scikit-learn metric (neighbors.py:239-243) is the Euclidean order of the standardised rows
+KNN_DEVICE_METRICS = ("euclidean", "l2", "minkowski", "correlation", "cosine")
 
 
-def knn(points, k: int, include_self: bool = False):
-    """Exact Euclidean k nearest neighbours of every row of ``points`` (C x D), ascending by distance.
-    Returns ``(idx int32 (C, k), dist float64 (C, k))`` CUDA tensors."""
+def knn(points, k: int, include_self: bool = False, metric: str = "euclidean"):
+    """Exact k nearest neighbours of every row of ``points`` (C x D), ascending by distance, under ``metric``
+    ("euclidean" | "correlation" | "cosine").  Returns ``(idx int32 (C, k), dist float64 (C, k))`` CUDA tensors;
+    ``dist`` is the metric's own distance (``1 - corr`` / ``1 - cos`` for the two angular metrics)."""
     device = require_cuda()
+    if metric not in KNN_DEVICE_METRICS:
+        raise ValueError(f"metric={metric!r} is not served by the device kNN ({KNN_DEVICE_METRICS})")
     X = (points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)))
     X = X.to(device=device, dtype=torch.float64).contiguous()
+    angular = metric in ("correlation", "cosine")
+    if angular:
+        if metric == "correlation":
+            X = X - X.mean(dim=1, keepdim=True)
+        X = (X / torch.linalg.vector_norm(X, dim=1, keepdim=True)).contiguous()
     C, D = X.shape
     idx = torch.empty((C, k), dtype=torch.int32, device=device)
     dist = torch.empty((C, k), dtype=torch.float64, device=device)
     _cabi.call("velo_dev_knn", X.data_ptr(), C, D, int(k), int(bool(include_self)), idx.data_ptr(), dist.data_ptr(),
                _stream_ptr())
+    if angular:
+        dist = dist * dist * 0.5
     return idx, dist
 
 

@@ -122,21 +122,38 @@ class BalancedKNN:
         self.constraint = constraint
         self.dist_new = self.dsi_new = self.l = None
         self.bknn = None
+        self._nn = None
 
     @property
     def n_samples(self) -> int:
         return self.data.shape[0]
 
+    def _device_metric(self):
+        """The metric as the device kernel knows it, or None when only scikit-learn implements it."""
+        from . import device as dev
+        if self.search != "device" or self.metric not in dev.KNN_DEVICE_METRICS:
+            return None
+        return "euclidean" if self.metric in ("l2", "minkowski") else self.metric
+
+    @property
+    def nn(self):
+        """scikit-learn searcher (neighbors.py:239-243), built on first use: the device search never needs it."""
+        if self._nn is None:
+            from sklearn.neighbors import NearestNeighbors
+            if self.metric == "correlation":
+                self._nn = NearestNeighbors(n_neighbors=self.sight_k + 1, metric=self.metric, n_jobs=self.n_jobs,
+                                            algorithm="brute")
+            else:
+                self._nn = NearestNeighbors(n_neighbors=self.sight_k + 1, metric=self.metric, n_jobs=self.n_jobs,
+                                            leaf_size=30)
+            self._nn.fit(self.fitdata)
+        return self._nn
+
     def fit(self, data: np.ndarray, sight_k: int = None):
-        from sklearn.neighbors import NearestNeighbors
         self.data = self.fitdata = data
         if sight_k is not None:
             self.sight_k = sight_k
-        if self.metric == "correlation":
-            self.nn = NearestNeighbors(n_neighbors=self.sight_k + 1, metric=self.metric, n_jobs=self.n_jobs, algorithm="brute")
-        else:
-            self.nn = NearestNeighbors(n_neighbors=self.sight_k + 1, metric=self.metric, n_jobs=self.n_jobs, leaf_size=30)
-        self.nn.fit(self.fitdata)
+        self._nn = None
         return self
 
     def kneighbors(self, X: np.ndarray = None, maxl: int = None, mode: str = "distance"):
@@ -145,12 +162,15 @@ class BalancedKNN:
         if maxl is not None:
             self.maxl = maxl
         from . import device as dev
-        if (self.search == "device" and self.metric != "correlation" and self.sight_k + 1 <= dev.KNN_MAX_K
-                and self.data is self.fitdata):
+        dev_metric = self._device_metric()
+        if (dev_metric is not None and self.sight_k + 1 <= dev.KNN_MAX_K and self.data is self.fitdata
+                and np.shape(self.fitdata)[1] <= 4096):
             # candidate lists (self included, ascending distance) from the brute-force device kernel
-            idx, dist = dev.knn(np.ascontiguousarray(self.fitdata, dtype=np.float64), self.sight_k + 1, include_self=True)
+            idx, dist = dev.knn(np.ascontiguousarray(self.fitdata, dtype=np.float64), self.sight_k + 1, include_self=True,
+                                metric=dev_metric)
             self.dist, self.dsi = dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64)
         else:
+            # any other scikit-learn metric ("manhattan", ...), queries other than the fitted data, oversized k
             self.dist, self.dsi = self.nn.kneighbors(self.data, return_distance=True)
         self.dist_new, self.dsi_new, self.l = knn_balance(self.dsi, self.dist, maxl=self.maxl, k=self.k,
                                                           constraint=self.constraint)

@@ -87,6 +87,99 @@ class CellShardedTransitionProb:
         return dev.transition_prob(corr, ix_local, self.sigma, c0=self.c0, out=corr)
 
 
+def _host_ptr(a):
+    """``(address, row pitch in elements, element bytes)`` of a 2-D host array (NumPy or CPU torch) whose rows are
+    contiguous -- e.g. a cell block ``M[:, c0:c0+nc]`` of the reference's gene-major matrix, passed without a copy."""
+    if isinstance(a, torch.Tensor):
+        assert not a.is_cuda and a.dim() == 2 and (a.stride(1) == 1 or a.shape[1] == 1)
+        assert a.dtype in (torch.float64, torch.float32, torch.int64)
+        return a.data_ptr(), a.stride(0) if a.shape[0] > 1 else a.shape[1], a.element_size()
+    import numpy as np
+    assert isinstance(a, np.ndarray) and a.ndim == 2 and (a.strides[1] == a.itemsize or a.shape[1] == 1)
+    assert a.dtype in (np.float64, np.float32, np.int64)
+    return a.ctypes.data, (a.strides[0] // a.itemsize) if a.shape[0] > 1 else a.shape[1], a.itemsize
+
+
+def needs_residuals(transform: str, psc: float, elem_bytes: int) -> bool:
+    """fp64 inputs + a transform that jumps at zero difference (sqrt with psc > 0, log10 with psc != 1): the fp32
+    residuals of ``e`` travel with it so that fp32 ties keep the fp64 sign (same rule as the one-GPU host tier)."""
+    import math
+    if elem_bytes != 8:
+        return False
+    if transform == "sqrt":
+        return 2.0 * math.sqrt(max(psc, 0.0)) > 1e-4
+    if transform in ("log", "log10"):
+        return 2.0 * abs(math.log10(psc if psc > 0 else 1e-300)) > 1e-4
+    return False
+
+
+class CellShardedHostTransitionProb:
+    """``velo_transition_prob_partial`` across the GPUs of one box, from HOST buffers in the reference's format.
+
+    Every rank calls :meth:`run` with its cell block: ``e_block`` / ``d_block`` gene-major ``(G, nc)`` float64 (or
+    float32) host arrays -- column blocks of the reference's matrices, NumPy views are fine, pinned or pageable --
+    ``ixs_block`` ``(nc, m)`` int64 GLOBAL neighbour ids and ``out_block`` ``(nc, m)`` float32.  Per rank:
+
+      1. ``velo_upload_cellmajor``: the expression block goes through PCIe straight into this rank's slot of the
+         gathered ``(world*b, ld)`` matrix (transpose + fp32 conversion on the device);
+      2. the path's one exchange step: an in-place NCCL all-gather of those slots over NVLink;
+      3. ``velo_transition_prob_partial_sharded``: velocity rows, neighbour lists and results move in cell chunks
+         underneath the correlation kernel; the first velocity chunk uploads while the all-gather is in flight.
+
+    Nothing but plumbing happens in Python (the reference's loop-level OpenMP parallelism,
+    speedboosted.pyx:22-23, at box scale)."""
+
+    def __init__(self, G: int, C: int, transform: str = "sqrt", psc: float = 1e-10, sigma: Optional[float] = 0.05,
+                 group=None):
+        self.G, self.C, self.transform, self.psc, self.sigma, self.group = G, C, transform, psc, sigma, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.b = block_size(C, self.world)
+        self.c0, self.nc = partition(C, self.world)[self.rank]
+        self._e_full = self._lo_full = None
+
+    def run(self, e_block, d_block, ixs_block, out_block):
+        from . import _cabi, device as dev
+        device = dev.require_cuda()
+        G, nc, b, ld = self.G, self.nc, self.b, dev.padded_ld(self.G)
+        e_ptr, e_pitch, e_sz = _host_ptr(e_block)
+        d_ptr, d_pitch, d_sz = _host_ptr(d_block)
+        ix_ptr, ix_pitch, ix_sz = _host_ptr(ixs_block)
+        o_ptr, o_pitch, o_sz = _host_ptr(out_block)
+        m = ixs_block.shape[1]
+        assert tuple(e_block.shape) == (G, nc) and tuple(d_block.shape) == (G, nc) and e_sz == d_sz
+        assert tuple(ixs_block.shape) == (nc, m) and tuple(out_block.shape) == (nc, m)
+        assert ix_sz == 8 and o_sz == 4 and ix_pitch == m and o_pitch == m
+        if self._e_full is None:
+            self._e_full = torch.zeros((self.world * b, ld), dtype=torch.float32, device=device)
+        want_lo = needs_residuals(self.transform, self.psc, e_sz)
+        if want_lo and self._lo_full is None:
+            self._lo_full = torch.zeros((self.world * b, ld), dtype=torch.float32, device=device)
+        stream = torch.cuda.current_stream().cuda_stream
+        mine = self._e_full[self.rank * b:(self.rank + 1) * b]
+        lo_mine = self._lo_full[self.rank * b:(self.rank + 1) * b] if want_lo else None
+        import ctypes
+        nz = ctypes.c_int(0)
+        if nc:
+            _cabi.call("velo_upload_cellmajor", e_ptr, e_sz, G, nc, e_pitch, mine.data_ptr(),
+                       0 if lo_mine is None else lo_mine.data_ptr(), ctypes.addressof(nz) if want_lo else 0, ld, stream)
+        use_lo = False
+        if want_lo:
+            flag = torch.tensor([nz.value], device=device, dtype=torch.int32)
+            if self.world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            use_lo = bool(flag.item())                      # any rank's block not fp32-representable
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._e_full, mine, group=self.group)          # in place: mine IS slot `rank`
+            if use_lo:
+                dist.all_gather_into_tensor(self._lo_full, lo_mine, group=self.group)
+        if nc:
+            _cabi.call("velo_transition_prob_partial_sharded", _cabi.TRANSFORMS[self.transform], self._e_full.data_ptr(),
+                       self._lo_full.data_ptr() if use_lo else 0, ld, stream, d_ptr, d_sz, d_pitch, ix_ptr, o_ptr,
+                       G, self.C, self.c0, nc, m, float(self.psc), float(self.sigma) if self.sigma else 0.0)
+        return out_block
+
+
 # --------------------------------------------------------------------------- gene-sharded stages (K4 / K5 / K6)
 def gene_partition(G: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
     """``(g0, ng)`` of every rank: contiguous gene blocks, starts aligned to ``align`` genes (128-byte rows)."""
