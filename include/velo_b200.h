@@ -321,6 +321,12 @@ int velo_dev_knn_smooth_csr(const int64_t *w_indptr, const int32_t *w_indices, c
  * analysis.py:1549); 1 keeps it (normally at rank 0; BalancedKNN's candidate lists, neighbors.py:282). k <= ~14000. */
 int velo_dev_knn(const double *X, int64_t C, int D, int k, int include_self,
                  int32_t *out_idx, double *out_dist, velo_stream_t stream);
+/* The same search for the query points [q0, q0 + nq) only (neighbours are still drawn from all C points): out_idx /
+ * out_dist are nq x k.  Queries are independent, so a multi-GPU caller gives every rank a block of queries and
+ * all-gathers the index blocks ("kNN search").  More than k/8+32 points tying at the k-th distance
+ * (duplicated points) are resolved by lowest index. */
+int velo_dev_knn_range(const double *X, int64_t C, int D, int k, int include_self, int64_t q0, int64_t nq,
+                       int32_t *out_idx, double *out_dist, velo_stream_t stream);
 
 /* ---- device-side randomisation (opt-in; the default keeps the reference's NumPy / numba streams on the host) ----
  * Weighted sampling without replacement of m of the W candidate neighbours of every cell (analysis.py:1552-1566, one

@@ -481,7 +481,7 @@ __global__ void k_scatter_dense(const float *__restrict__ out, int64_t out_ld, c
 __global__ void __launch_bounds__(256) k_transition_prob(const float *__restrict__ corr, int64_t ld,
                                                          const int32_t *__restrict__ ixs, int64_t ixs_ld,
                                                          float *__restrict__ p, int64_t p_ld, int64_t c0, int64_t nc,
-                                                         int64_t m, float inv_sigma, int patch_nan)
+                                                         int64_t m, double inv_sigma, int patch_nan)
 {
     const int lane = threadIdx.x & 31;
     const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -510,14 +510,18 @@ __global__ void __launch_bounds__(256) k_transition_prob(const float *__restrict
         const int64_t i = ixs ? static_cast<int64_t>(ixs[r * ixs_ld + n]) : n;
         if (i == self) v = 0.0f;
         else if (v != v) v = 1.0f;
-        const float ex = expf((v - vmax) * inv_sigma);
-        pr[n] = ex;
-        sum += static_cast<double>(ex);
+        // exponent and exp in fp64, like the reference: in fp32 the rounding of (v - vmax) / sigma alone is |x| * 6e-8
+        // relative on exp(x) (2.4e-6 at x = -40, i.e. sigma = 0.05 and opposite correlations); 40 DFMA per element
+        // are nothing next to the correlation kernel that produced it
+        const double exd = exp(static_cast<double>(v - vmax) * inv_sigma);
+        pr[n] = static_cast<float>(exd);
+        sum += exd;
     }
     sum = warp_sum(sum);
-    const float inv = bad ? __int_as_float(0x7fc00000) : static_cast<float>(1.0 / sum);
+    const double inv = 1.0 / sum;
     __syncwarp();
-    for (int64_t n = lane; n < m; n += 32) pr[n] *= inv;
+    for (int64_t n = lane; n < m; n += 32)
+        pr[n] = bad ? __int_as_float(0x7fc00000) : static_cast<float>(static_cast<double>(pr[n]) * inv);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -653,7 +657,7 @@ extern "C" int velo_dev_transition_prob_ex(const float *corr, int64_t ld, const 
     if (nc == 0) return VELO_OK;
     const int wpb = 8;
     k_transition_prob<<<static_cast<unsigned>((nc + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(
-        corr, ld, ixs, ixs_ld, p, p_ld, c0, nc, m, static_cast<float>(1.0 / sigma), patch_nan);
+        corr, ld, ixs, ixs_ld, p, p_ld, c0, nc, m, 1.0 / sigma, patch_nan);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }

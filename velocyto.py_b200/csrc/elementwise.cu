@@ -98,20 +98,50 @@ __global__ void __launch_bounds__(256) k_velocity_chain(const ChainParams p)
     }
 }
 
-// per-gene max over cells of gamma*S + q (for the eps threshold of calculate_velocity)
+// per-gene max over cells of gamma*S + q (for the eps threshold of calculate_velocity, analysis.py:1377-1378).
+// grid = (gene blocks, cell slices): lanes = adjacent genes (coalesced 128-byte lines), every CTA scans one slice of the
+// cell axis with 4 independent running maxima, slices merge through an order-preserving integer atomicMax.
+__device__ __forceinline__ unsigned int f2ord(float f)
+{
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 __global__ void __launch_bounds__(128) k_gene_max_upred(const float *__restrict__ S, int64_t ld, const float *__restrict__ gamma,
                                                         const float *__restrict__ q, int64_t G, int64_t C,
-                                                        float eps, float *__restrict__ thr)
+                                                        unsigned int *__restrict__ mx_ord)
 {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (g >= G) return;
     const float gam = gamma[g], qq = q ? q[g] : 0.f;
-    float mx = -INFINITY;
-    for (int64_t c = 0; c < C; ++c) mx = fmaxf(mx, fmaf(gam, S[c * ld + g], qq));
-    thr[g] = mx * eps;
+    const int64_t per = (C + gridDim.y - 1) / gridDim.y;
+    const int64_t c0 = static_cast<int64_t>(blockIdx.y) * per, c1 = min(C, c0 + per);
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    int64_t c = c0;
+    for (; c + 4 <= c1; c += 4) {
+        m0 = fmaxf(m0, fmaf(gam, S[c * ld + g], qq));
+        m1 = fmaxf(m1, fmaf(gam, S[(c + 1) * ld + g], qq));
+        m2 = fmaxf(m2, fmaf(gam, S[(c + 2) * ld + g], qq));
+        m3 = fmaxf(m3, fmaf(gam, S[(c + 3) * ld + g], qq));
+    }
+    for (; c < c1; ++c) m0 = fmaxf(m0, fmaf(gam, S[c * ld + g], qq));
+    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    if (c1 > c0) atomicMax(mx_ord + g, f2ord(mx));      // NaN (gamma = NaN) orders above +inf: propagates like np.max
+}
+__global__ void k_gene_max_finalize(const unsigned int *__restrict__ mx_ord, int64_t G, float eps, float *__restrict__ thr)
+{
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g < G) thr[g] = ord2f(mx_ord[g]) * eps;
 }
 
-// one CTA row-segment: cell c, 1024 genes; thread = one float4 of genes, loops over the cell's neighbours
+// one CTA row-segment: cell c, 1024 genes; thread = one float4 of genes, loops over the cell's neighbours.
+// Accumulation: the four products of a group of 4 neighbours are summed pairwise in fp32 and the group sum is folded
+// into an fp64 accumulator -- one fp32->fp64 conversion per 4 neighbours instead of five (round 1 converted every
+// gathered value: the conversions issue on the 16-lane XU pipe, which ncu showed 87 % busy).  Error of a group sum
+// <= 3 fp32 roundings of same-sign terms (~1e-7 relative, unbiased); the fp64 fold keeps it from growing with k.
 __global__ void __launch_bounds__(256) k_knn_smooth(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                                                     const float *__restrict__ weights, const float *__restrict__ S,
                                                     float *__restrict__ out, int64_t ld, int64_t G, int maximum)
@@ -122,22 +152,26 @@ __global__ void __launch_bounds__(256) k_knn_smooth(const int64_t *__restrict__ 
     const int64_t p0 = indptr[c], p1 = indptr[c + 1];
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int64_t p = p0;
-    for (; p + 4 <= p1; p += 4) {                         // 4 independent row loads in flight
-        const int32_t j0 = indices[p], j1 = indices[p + 1], j2 = indices[p + 2], j3 = indices[p + 3];
-        const float w0 = weights[p], w1 = weights[p + 1], w2 = weights[p + 2], w3 = weights[p + 3];
-        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(S + static_cast<int64_t>(j0) * ld + g));
-        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(S + static_cast<int64_t>(j1) * ld + g));
-        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(S + static_cast<int64_t>(j2) * ld + g));
-        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(S + static_cast<int64_t>(j3) * ld + g));
-        a0 += (double)w0 * v0.x + (double)w1 * v1.x + (double)w2 * v2.x + (double)w3 * v3.x;
-        a1 += (double)w0 * v0.y + (double)w1 * v1.y + (double)w2 * v2.y + (double)w3 * v3.y;
-        a2 += (double)w0 * v0.z + (double)w1 * v1.z + (double)w2 * v2.z + (double)w3 * v3.z;
-        a3 += (double)w0 * v0.w + (double)w1 * v1.w + (double)w2 * v2.w + (double)w3 * v3.w;
+    for (; p + 8 <= p1; p += 8) {                         // 8 independent row loads in flight, two groups of 4
+        float4 v[8];
+        float w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            w[k] = weights[p + k];
+            v[k] = __ldg(reinterpret_cast<const float4 *>(S + static_cast<int64_t>(indices[p + k]) * ld + g));
+        }
+#pragma unroll
+        for (int h = 0; h < 8; h += 4) {
+            a0 += static_cast<double>(fmaf(w[h], v[h].x, w[h + 1] * v[h + 1].x) + fmaf(w[h + 2], v[h + 2].x, w[h + 3] * v[h + 3].x));
+            a1 += static_cast<double>(fmaf(w[h], v[h].y, w[h + 1] * v[h + 1].y) + fmaf(w[h + 2], v[h + 2].y, w[h + 3] * v[h + 3].y));
+            a2 += static_cast<double>(fmaf(w[h], v[h].z, w[h + 1] * v[h + 1].z) + fmaf(w[h + 2], v[h + 2].z, w[h + 3] * v[h + 3].z));
+            a3 += static_cast<double>(fmaf(w[h], v[h].w, w[h + 1] * v[h + 1].w) + fmaf(w[h + 2], v[h + 2].w, w[h + 3] * v[h + 3].w));
+        }
     }
     for (; p < p1; ++p) {
         const float w = weights[p];
         const float4 v = __ldg(reinterpret_cast<const float4 *>(S + static_cast<int64_t>(indices[p]) * ld + g));
-        a0 += (double)w * v.x; a1 += (double)w * v.y; a2 += (double)w * v.z; a3 += (double)w * v.w;
+        a0 += (double)(w * v.x); a1 += (double)(w * v.y); a2 += (double)(w * v.z); a3 += (double)(w * v.w);
     }
     float4 r = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
     if (maximum) {                                        // np.maximum(S_sz, Sx), analysis.py:1017-1019
@@ -306,9 +340,24 @@ extern "C" int velo_dev_velocity_threshold(const float *S_cm, int64_t ld, const 
                                            int64_t G, int64_t C, double eps, float *thr, velo_stream_t stream)
 {
     VELO_REQUIRE(S_cm && gamma && thr && G > 0 && C > 0 && ld >= G, "velocity_threshold: bad arguments");
-    k_gene_max_upred<<<static_cast<unsigned>((G + 127) / 128), 128, 0, as_stream(stream)>>>(
-        S_cm, ld, gamma, q, G, C, static_cast<float>(eps), thr);
-    VELO_LAUNCH_CHECK();
+    cudaStream_t st = as_stream(stream);
+    unsigned int *mx = nullptr;
+    VELO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&mx), static_cast<size_t>(G) * 4, st));
+    cudaError_t e = cudaMemsetAsync(mx, 0, static_cast<size_t>(G) * 4, st);         // 0 orders below every float
+    if (e == cudaSuccess) {
+        const int64_t gx = (G + 127) / 128;
+        int64_t gy = (148 * 16 + gx - 1) / gx;                                      // ~16 CTAs per SM in total
+        if (gy > (C + 63) / 64) gy = (C + 63) / 64;
+        if (gy < 1) gy = 1;
+        dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+        k_gene_max_upred<<<grid, 128, 0, st>>>(S_cm, ld, gamma, q, G, C, mx);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        k_gene_max_finalize<<<static_cast<unsigned>(gx), 128, 0, st>>>(mx, G, static_cast<float>(eps), thr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(mx, st);
+    VELO_CUDA_TRY(e);
     return VELO_OK;
 }
 

@@ -21,7 +21,7 @@ __device__ __forceinline__ uint32_t knn_f2key(float f)   // f >= 0
 
 struct KnnParams {
     const double *X;       // C x D
-    int64_t C;
+    int64_t C, q0, nq;     // points; query range [q0, q0 + nq)
     int D, k, include_self, P;
     int32_t *out_idx;      // C x k
     double *out_dist;      // C x k or null
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
     uint32_t *keys = p.scratch + static_cast<int64_t>(blockIdx.x) * p.C;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
-    for (int64_t q = blockIdx.x; q < p.C; q += gridDim.x) {
+    for (int64_t q = p.q0 + blockIdx.x; q < p.q0 + p.nq; q += gridDim.x) {
         for (int d = tid; d < p.D; d += nt) xq[d] = p.X[q * p.D + d];
         __syncthreads();
         // 1. distances -> keys
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
                 __syncthreads();
             }
         for (int r = tid; r < p.k; r += nt) {
-            p.out_idx[q * p.k + r] = c_idx[r];
-            if (p.out_dist) p.out_dist[q * p.k + r] = sqrt(c_key[r]);
+            p.out_idx[(q - p.q0) * p.k + r] = c_idx[r];
+            if (p.out_dist) p.out_dist[(q - p.q0) * p.k + r] = sqrt(c_key[r]);
         }
         __syncthreads();
     }
@@ -198,7 +198,15 @@ using namespace velo;
 extern "C" int velo_dev_knn(const double *X, int64_t C, int D, int k, int include_self, int32_t *out_idx,
                             double *out_dist, velo_stream_t stream)
 {
+    return velo_dev_knn_range(X, C, D, k, include_self, 0, C, out_idx, out_dist, stream);
+}
+
+extern "C" int velo_dev_knn_range(const double *X, int64_t C, int D, int k, int include_self, int64_t q0, int64_t nq,
+                                  int32_t *out_idx, double *out_dist, velo_stream_t stream)
+{
     VELO_REQUIRE(X && out_idx && C > 0 && D > 0 && D <= 4096, "knn: bad arguments");
+    VELO_REQUIRE(q0 >= 0 && nq >= 0 && q0 + nq <= C, "knn: query range outside [0, %lld)", static_cast<long long>(C));
+    if (nq == 0) return VELO_OK;
     VELO_REQUIRE(k > 0 && k <= (include_self ? C : C - 1), "knn: k = %d out of range for %lld points", k,
                  static_cast<long long>(C));
     VELO_REQUIRE(C < 2147483647LL, "knn: too many points");
@@ -214,14 +222,14 @@ extern "C" int velo_dev_knn(const double *X, int64_t C, int D, int k, int includ
     int per_sm = 1;
     VELO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_knn_bruteforce, 512, smem));
     int64_t grid = static_cast<int64_t>(dp.sm_count) * (per_sm > 0 ? per_sm : 1);
-    if (grid > C) grid = C;
+    if (grid > nq) grid = nq;
     uint32_t *scratch = nullptr;
     int *overflow = nullptr;
     VELO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), static_cast<size_t>(grid) * C * 4, st));
     VELO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&overflow), sizeof(int), st));
     VELO_CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int), st));
     KnnParams p;
-    p.X = X; p.C = C; p.D = D; p.k = k; p.include_self = include_self; p.P = P;
+    p.X = X; p.C = C; p.q0 = q0; p.nq = nq; p.D = D; p.k = k; p.include_self = include_self; p.P = P;
     p.out_idx = out_idx; p.out_dist = out_dist; p.scratch = scratch; p.overflow = overflow;
     k_knn_bruteforce<<<static_cast<unsigned>(grid), 512, smem, st>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);

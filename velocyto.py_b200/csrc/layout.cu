@@ -29,8 +29,13 @@ __global__ void __launch_bounds__(256) k_pack_cellmajor(const T *__restrict__ sr
             nz |= lo != 0.0f;
         }
     }
-    if (SPLIT && nz) atomicExch(nz_flag, 1);
-    __syncthreads();
+    // one flag write per CTA at most, and none once the flag is up: round 1 let EVERY thread with a non-zero residual
+    // hit the same address (8 M same-address atomics per 256 MB chunk, ~0.4 s over a 24 GB upload)
+    if (SPLIT) {
+        if (__syncthreads_or(nz) && threadIdx.x == 0 && *reinterpret_cast<volatile int *>(nz_flag) == 0) atomicExch(nz_flag, 1);
+    } else {
+        __syncthreads();
+    }
 #pragma unroll
     for (int k = 0; k < 32; k += 8) {
         const int64_t c = c0 + ty + k, g = g0 + tx;           // coalesced over genes (destination rows)

@@ -130,14 +130,48 @@ __device__ double block_percentile(const float *__restrict__ row, int64_t n, dou
     return r;
 }
 
+// Stage a gene row in shared memory: every order statistic makes 5+ passes over its row, and np.percentile is asked
+// for 2-3 of them per gene.  TMA bulk copies (cp.async.bulk, completion on an mbarrier) when the row is 16-byte aligned,
+// a cooperative copy otherwise.  *bar must be initialised (count 1) and is used for exactly one phase.
+__device__ __forceinline__ const float *stage_row(const float *__restrict__ row, float *s_row, int64_t C, uint64_t *bar)
+{
+    const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) && (C % 4 == 0);
+    if (aligned) {
+        if (threadIdx.x == 0) {
+            const uint32_t total = static_cast<uint32_t>(C * 4);
+            mbar_expect_tx(bar, total);
+            for (uint32_t off = 0; off < total; off += 32768u) {
+                const uint32_t n = total - off < 32768u ? total - off : 32768u;
+                tma_load_1d(reinterpret_cast<unsigned char *>(s_row) + off, reinterpret_cast<const unsigned char *>(row) + off, n, bar);
+            }
+        }
+        mbar_wait(bar, 0);
+    } else {
+        for (int64_t i = threadIdx.x; i < C; i += blockDim.x) s_row[i] = row[i];
+        __syncthreads();
+    }
+    return s_row;
+}
+
 // out[g*nq + j] = np.percentile(rows[g, :], q[j])
 __global__ void __launch_bounds__(256) k_row_percentiles(const float *__restrict__ rows, int64_t G, int64_t C,
-                                                         const double *__restrict__ q, int nq, double *__restrict__ out)
+                                                         const double *__restrict__ q, int nq, double *__restrict__ out,
+                                                         int in_smem)
 {
+    extern __shared__ __align__(128) unsigned char q_smem[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long scratch[4];
+    __shared__ uint64_t bar;
     const int64_t g = blockIdx.x;
     const float *row = rows + g * C;
+    if (in_smem) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        row = stage_row(row, reinterpret_cast<float *>(q_smem), C, &bar);
+    }
     for (int j = 0; j < nq; ++j) {
         const double r = block_percentile(row, C, q[j], AllOf(), false, hist, scratch);
         if (threadIdx.x == 0) out[g * nq + j] = r;
@@ -267,7 +301,18 @@ extern "C" int velo_dev_row_percentiles(const float *rows_gc, int64_t G, int64_t
 {
     VELO_REQUIRE(rows_gc && q_dev && out && G > 0 && C > 0 && nq > 0, "row_percentiles: bad arguments");
     VELO_REQUIRE(G <= 2147483647LL, "row_percentiles: too many rows");
-    k_row_percentiles<<<static_cast<unsigned>(G), 256, 0, as_stream(stream)>>>(rows_gc, G, C, q_dev, nq, out);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc) return rc;
+    const size_t row_bytes = (static_cast<size_t>(C) * 4 + 15) / 16 * 16;
+    // rows up to 72 KB (18k cells): >= 3 CTAs per SM stay resident; longer rows keep streaming from L2, where 8 CTAs
+    // per SM hide the latency better than one CTA could from shared memory
+    const int in_smem = row_bytes <= (72u << 10) && row_bytes + 4096 <= static_cast<size_t>(dp.smem_optin) ? 1 : 0;
+    if (in_smem)
+        VELO_CUDA_TRY(cudaFuncSetAttribute(k_row_percentiles, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(row_bytes)));
+    k_row_percentiles<<<static_cast<unsigned>(G), 256, in_smem ? row_bytes : 0, as_stream(stream)>>>(rows_gc, G, C, q_dev,
+                                                                                                  nq, out, in_smem);
     VELO_LAUNCH_CHECK();
     return VELO_OK;
 }

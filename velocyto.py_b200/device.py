@@ -434,10 +434,12 @@ KNN_MAX_K = 14000
 KNN_DEVICE_METRICS = ("euclidean", "l2", "minkowski", "correlation", "cosine")
 
 
-def knn(points, k: int, include_self: bool = False, metric: str = "euclidean"):
+def knn(points, k: int, include_self: bool = False, metric: str = "euclidean", q0: int = 0, nq: Optional[int] = None,
+        want_dist: bool = True):
     """Exact k nearest neighbours of every row of ``points`` (C x D), ascending by distance, under ``metric``
     ("euclidean" | "correlation" | "cosine").  Returns ``(idx int32 (C, k), dist float64 (C, k))`` CUDA tensors;
-    ``dist`` is the metric's own distance (``1 - corr`` / ``1 - cos`` for the two angular metrics)."""
+    ``dist`` is the metric's own distance (``1 - corr`` / ``1 - cos`` for the two angular metrics).
+    ``q0`` / ``nq``: only the query block ``[q0, q0 + nq)`` (rank-sharded searches)."""
     device = require_cuda()
     if metric not in KNN_DEVICE_METRICS:
         raise ValueError(f"metric={metric!r} is not served by the device kNN ({KNN_DEVICE_METRICS})")
@@ -449,11 +451,12 @@ def knn(points, k: int, include_self: bool = False, metric: str = "euclidean"):
             X = X - X.mean(dim=1, keepdim=True)
         X = (X / torch.linalg.vector_norm(X, dim=1, keepdim=True)).contiguous()
     C, D = X.shape
-    idx = torch.empty((C, k), dtype=torch.int32, device=device)
-    dist = torch.empty((C, k), dtype=torch.float64, device=device)
-    _cabi.call("velo_dev_knn", X.data_ptr(), C, D, int(k), int(bool(include_self)), idx.data_ptr(), dist.data_ptr(),
-               _stream_ptr())
-    if angular:
+    nq = C - q0 if nq is None else nq
+    idx = torch.empty((nq, k), dtype=torch.int32, device=device)
+    dist = torch.empty((nq, k), dtype=torch.float64, device=device) if want_dist else None
+    _cabi.call("velo_dev_knn_range", X.data_ptr(), C, D, int(k), int(bool(include_self)), int(q0), int(nq), idx.data_ptr(),
+               0 if dist is None else dist.data_ptr(), _stream_ptr())
+    if angular and dist is not None:
         dist = dist * dist * 0.5
     return idx, dist
 
