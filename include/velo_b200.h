@@ -328,6 +328,16 @@ int velo_dev_knn(const double *X, int64_t C, int D, int k, int include_self,
 int velo_dev_knn_range(const double *X, int64_t C, int D, int k, int include_self, int64_t q0, int64_t nq,
                        int32_t *out_idx, double *out_dist, velo_stream_t stream);
 
+/* Neighbours of nq separate QUERY points Q (nq x D fp64, device) among the C points of X -- the grid-point search of
+ * calculate_grid_arrows (analysis.py:1788-1790: NearestNeighbors.fit(embedding).kneighbors(gridpoints)). */
+int velo_dev_knn_query(const double *X, int64_t C, int D, const double *Q, int64_t nq, int k,
+                       int32_t *out_idx, double *out_dist, velo_stream_t stream);
+/* calculate_grid_arrows core (analysis.py:1792-1797): gaussian kernel weights w = normal.pdf(dists, scale = sigma) of
+ * every grid point's k nearest cells, mass[p] = sum_n w, flow[p, :] = sum_n w * delta[neighs[p, n], :] / max(1, mass[p]).
+ * neighs / dists: npts x k (from velo_dev_knn_query); delta: cells x dims fp64 (delta_embedding); outputs fp64. */
+int velo_dev_grid_flow(const int32_t *neighs, const double *dists, int64_t npts, int k, const double *delta,
+                       int dims, double sigma, double *mass, double *flow, velo_stream_t stream);
+
 /* ---- device-side randomisation (opt-in; the default keeps the reference's NumPy / numba streams on the host) ----
  * Weighted sampling without replacement of m of the W candidate neighbours of every cell (analysis.py:1552-1566, one
  * np.random.choice(W, m, replace=False, p) per cell): same distribution (successive sampling, order included) through

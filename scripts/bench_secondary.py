@@ -55,6 +55,15 @@ def main():
     report("k_velocity_chain (K6, 5 outputs)", ms, 7 * C * G * 4, shape=f"{C}x{G}")
     ms = timeit(lambda: dev.velocity_chain(Sx, Ux, g, q, transform="sqrt", psc=1.0, want=("d",)))
     report("k_velocity_chain (K6, d only)", ms, 3 * C * G * 4, shape=f"{C}x{G}")
+    ms = timeit(lambda: dev.velocity_chain(Sx, Ux, g, q, transform="sqrt", psc=1.0, eps=0.05, want=("velocity",)))
+    report("velocity threshold (k_gene_max_upred) + k_velocity_chain (velocity only, eps)", ms, 4 * C * G * 4, shape=f"{C}x{G}")
+    # normalize family
+    sums = dev.cell_sums(S)
+    fac = (sums.mean() / sums).contiguous()
+    ms = timeit(lambda: dev.size_normalize(S, fac, 1.0))
+    report("k_size_normalize (S_sz + S_norm in one pass)", ms, 3 * C * G * 4, shape=f"{C}x{G}")
+    ms = timeit(lambda: dev.cell_sums(S))
+    report("k_cell_sums", ms, C * G * 4, shape=f"{C}x{G}")
     # layout converters
     src = torch.rand((4096, C), device="cuda", dtype=torch.float64)
     dst = dev.CellMajor.empty(C, 4096)

@@ -252,6 +252,70 @@ def golden_pipeline(an, out):
     np.savez_compressed(os.path.join(out, "pipeline_small.npz"), **res)
 
 
+def golden_pipeline_medium(an, out):
+    """The whole tutorial chain (doc/tutorial/analysis.rst:108-165) through the reference's OWN methods at a size where
+    fp32 storage roundings average out (>= 1000 genes): normalize -> perform_PCA (scikit-learn) -> knn_imputation ->
+    fit_gammas -> predict_U -> calculate_velocity -> calculate_shift -> extrapolate_cell_at_t ->
+    estimate_transition_prob (psc = 1 as in the tutorial, and the default psc = 1e-10) -> calculate_embedding_shift ->
+    calculate_grid_arrows.  Stored compactly: inputs, per-gene vectors, per-cell x neighbour matrices, a 40-gene
+    slice of the big matrices."""
+    if an is None:
+        print("skipping medium pipeline golden (analysis.py not importable)")
+        return
+    import warnings
+    G, C = 1400, 260
+    S, U = synth_counts(G, C, 31)
+    keep = (S.sum(1) > 3) & (U.sum(1) > 3)
+    S, U = S[keep][:1100], U[keep][:1100]
+    G = S.shape[0]
+    vlm = an.VelocytoLoom.__new__(an.VelocytoLoom)
+    vlm.S, vlm.U, vlm.A = S, U, np.zeros_like(S)
+    vlm.ca, vlm.ra = {"CellID": np.arange(C)}, {"Gene": np.arange(G)}
+    vlm.initial_cell_size = S.sum(0)
+    vlm.initial_Ucell_size = U.sum(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vlm.normalize("both", size=True, log=True)
+    vlm.perform_PCA(n_components=12)
+    res = {"S": S, "U": U, "pcs": vlm.pcs.copy(), "pca_explained_variance_ratio": vlm.pca.explained_variance_ratio_.copy(),
+           "pca_explained_variance": vlm.pca.explained_variance_.copy(), "pca_components_head": vlm.pca.components_[:, :60].copy()}
+    vlm.knn_imputation(k=25, pca_space=True, n_pca_dims=10, balanced=False, n_jobs=1)
+    res.update(knn_data=vlm.knn.data, knn_indices=vlm.knn.indices, knn_indptr=vlm.knn.indptr)
+    for a in ("Sx", "Ux", "Sx_sz", "Ux_sz"):                   # C-contiguous, as a gene filter leaves them (SURVEY.md 3.1)
+        setattr(vlm, a, np.ascontiguousarray(getattr(vlm, a)))
+    res["Sx_sz_head"], res["Ux_sz_head"] = vlm.Sx_sz[:40].copy(), vlm.Ux_sz[:40].copy()
+    vlm.fit_gammas(weighted=False, fit_offset=False)
+    res["gammas_nnls"] = vlm.gammas.copy()
+    vlm.fit_gammas()                                           # default: maxmin_diag weights + offset (L-BFGS-B iterate)
+    res["gammas_default"], res["q_default"] = vlm.gammas.copy(), vlm.q.copy()
+    vlm.fit_gammas(weighted=False, fit_offset=True)            # the chain continues from the OLS fit (parity-able to 1e-5)
+    res["gammas_ols"], res["q_ols"] = vlm.gammas.copy(), vlm.q.copy()
+    vlm.predict_U()
+    vlm.calculate_velocity()
+    vlm.calculate_shift(assumption="constant_velocity")
+    vlm.extrapolate_cell_at_t(delta_t=1.0)
+    res.update(Upred_head=vlm.Upred[:40].copy(), velocity_head=vlm.velocity[:40].copy(), delta_S_head=vlm.delta_S[:40].copy(),
+               Sx_sz_t_head=vlm.Sx_sz_t[:40].copy())
+    vlm.ts = vlm.pcs[:, :2].copy()
+    rows = np.arange(C)[:, None]
+    for tag, psc in (("psc1", 1), ("pscdef", None)):
+        vlm.estimate_transition_prob(hidim="Sx_sz", embed="ts", transform="sqrt", psc=psc, n_neighbors=80,
+                                     knn_random=True, sampled_fraction=0.5, n_jobs=1, threads=1)
+        vlm.calculate_embedding_shift(sigma_corr=0.05, expression_scaling=True)
+        nb_ix = vlm.embedding_knn.indices.reshape(C, -1).copy()
+        res.update({f"{tag}_neigh_ixs": nb_ix, f"{tag}_sampling_ixs": vlm.sampling_ixs.copy(),
+                    f"{tag}_corrcoef": vlm.corrcoef[rows, nb_ix].copy(), f"{tag}_corrcoef_random": vlm.corrcoef_random[rows, nb_ix].copy(),
+                    f"{tag}_transition_prob": vlm.transition_prob[rows, nb_ix].copy(),
+                    f"{tag}_transition_prob_random": vlm.transition_prob_random[rows, nb_ix].copy(),
+                    f"{tag}_delta_embedding": vlm.delta_embedding.copy(), f"{tag}_delta_embedding_random": vlm.delta_embedding_random.copy(),
+                    f"{tag}_scaling": vlm.scaling.copy()})
+    vlm.delta_ts, vlm.delta_ts_random = vlm.delta_embedding, vlm.delta_embedding_random     # what the tutorial's plots read
+    vlm.calculate_grid_arrows(embed="ts", smooth=0.8, steps=(14, 11), n_neighbors=40, n_jobs=1)
+    res.update(flow_grid=vlm.flow_grid, flow=vlm.flow, total_p_mass=vlm.total_p_mass, flow_norm=vlm.flow_norm,
+               flow_norm_magnitude=vlm.flow_norm_magnitude, flow_rndm=vlm.flow_rndm, flow_norm_rndm=vlm.flow_norm_rndm)
+    np.savez_compressed(os.path.join(out, "pipeline_medium.npz"), **res)
+
+
 def golden_normalize(an, out):
     """The size/log normalisation family (analysis.py:535-676) on hand-built objects."""
     if an is None:
@@ -299,11 +363,15 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "normalize":     # add one fixture without touching the others
         golden_normalize(an, HERE)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "medium":
+        golden_pipeline_medium(an, HERE)
+        return
     golden_normalize(an, HERE)
     golden_coldeltacor(est, HERE)
     golden_fits(est, an, HERE)
     golden_smoothing(nb, HERE)
     golden_pipeline(an, HERE)
+    golden_pipeline_medium(an, HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

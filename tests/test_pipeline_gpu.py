@@ -606,3 +606,234 @@ def test_estimate_transition_prob_device_random_backend(golden):
     want = vo.patch_corrcoef(want)
     rows = np.arange(C)[:, None]
     np.testing.assert_allclose(vlm.corrcoef[rows, vlm.neigh_ixs], want[rows, vlm.neigh_ixs], rtol=0, atol=5e-6)
+
+
+# --------------------------------------------------------------------------- round 2: >= 1000 genes through the API
+def _oracle_chain_medium(vo, g):
+    """The reference chain restated by the (pinned) oracle on the golden counts, in fp64: the full-size matrices the
+    medium fixture only stores a 40-gene head of."""
+    S, U = g["S"], g["U"]
+    S_sz = vo.size_log_normalize(S)[0]
+    U_sz = vo.size_log_normalize(U, guard=True)[0]
+    C = S.shape[1]
+    knn = sparse.csr_matrix((g["knn_data"], g["knn_indices"], g["knn_indptr"]), shape=(C, C))
+    Sx, Ux = vo.knn_imputation(S_sz, U_sz, knn)
+    gam, q = vo.fit_slope_offset(np.ascontiguousarray(Ux), np.ascontiguousarray(Sx))
+    Upred = vo.predict_U(gam, Sx, q)
+    dS = vo.calculate_shift(vo.calculate_velocity(Ux, Upred), 1.0)
+    return np.ascontiguousarray(Sx), np.ascontiguousarray(Ux), gam, q, Upred, dS
+
+
+def test_velocytoloom_medium_pipeline_matches_reference_golden(golden, oracle):
+    """The tutorial chain through VelocytoLoom at 1100 genes x 260 cells against vectors produced by the reference's
+    own methods (tests/golden/make_golden.py::golden_pipeline_medium): gamma, predicted U and the transition
+    probabilities at the north-star 1e-5, THROUGH the API."""
+    from velocyto_b200.analysis import VelocytoLoom
+    g = golden("pipeline_medium.npz")
+    S, U = g["S"], g["U"]
+    G, C = S.shape
+    vlm = VelocytoLoom(S=S, U=U)
+    vlm.normalize("both", size=True, log=True)
+    # ---- PCA on the device vs scikit-learn's (exact "full" solver at this size)
+    vlm.perform_PCA(n_components=12)
+    scale = np.abs(g["pcs"]).max()
+    np.testing.assert_allclose(vlm.pcs, g["pcs"], rtol=0, atol=2e-6 * scale)
+    np.testing.assert_allclose(vlm.pca.explained_variance_ratio_, g["pca_explained_variance_ratio"], rtol=1e-5)
+    np.testing.assert_allclose(vlm.pca.explained_variance_, g["pca_explained_variance"], rtol=1e-5)
+    np.testing.assert_allclose(vlm.pca.components_[:, :60], g["pca_components_head"], rtol=0, atol=2e-6)
+    vlm.pcs = g["pcs"]                       # continue from the reference's components: stage-by-stage identical inputs
+    vlm.knn_imputation(k=25, pca_space=True, n_pca_dims=10, balanced=False, n_jobs=1)
+    knn_sorted = vlm.knn.copy()
+    knn_sorted.sort_indices()
+    assert np.array_equal(knn_sorted.indices, g["knn_indices"])
+    np.testing.assert_allclose(vlm.Sx_sz[:40], g["Sx_sz_head"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(vlm.Ux_sz[:40], g["Ux_sz_head"], rtol=1e-6, atol=1e-7)
+    vlm.fit_gammas(weighted=False, fit_offset=False)
+    np.testing.assert_allclose(vlm.gammas, g["gammas_nnls"], rtol=1e-5, atol=1e-8)          # gamma, 1e-5
+    vlm.fit_gammas(weighted=False, fit_offset=True)
+    np.testing.assert_allclose(vlm.gammas, g["gammas_ols"], rtol=1e-5, atol=2e-6)            # (leastsq itself: ~1e-5)
+    np.testing.assert_allclose(vlm.q, g["q_ols"], rtol=1e-5, atol=2e-5)
+    vlm.predict_U()
+    vlm.calculate_velocity()
+    vlm.calculate_shift(assumption="constant_velocity")
+    vlm.extrapolate_cell_at_t(delta_t=1.0)
+    np.testing.assert_allclose(vlm.Upred[:40], g["Upred_head"], rtol=1e-5, atol=2e-5)        # predicted U, 1e-5
+    np.testing.assert_allclose(vlm.velocity[:40], g["velocity_head"], rtol=1e-5, atol=3e-5)
+    np.testing.assert_allclose(vlm.Sx_sz_t[:40], g["Sx_sz_t_head"], rtol=1e-5, atol=3e-5)
+    vlm.ts = g["pcs"][:, :2].copy()
+    kw = dict(hidim="Sx_sz", embed="ts", transform="sqrt", n_neighbors=80, knn_random=True, sampled_fraction=0.5,
+              n_jobs=1, threads=1)
+    # ---- default psc (1e-10: the transforms are continuous): the WHOLE chain ran through our methods
+    vlm.estimate_transition_prob(psc=None, **kw)
+    assert np.array_equal(vlm.neigh_ixs, g["pscdef_neigh_ixs"]) and np.array_equal(vlm.sampling_ixs, g["pscdef_sampling_ixs"])
+    np.testing.assert_allclose(vlm.corrcoef_compact, g["pscdef_corrcoef"], rtol=0, atol=1e-6)
+    vlm.calculate_embedding_shift(sigma_corr=0.05, expression_scaling=True)
+    np.testing.assert_allclose(vlm.transition_prob_compact, g["pscdef_transition_prob"], rtol=2e-5, atol=0)
+    # ---- identical inputs (the reference's own Sx_sz / delta_S, restated by the pinned oracle in fp64):
+    #      estimate_transition_prob + calculate_embedding_shift through the API at the north-star 1e-5
+    Sx, Ux, gam, q, Upred, dS = _oracle_chain_medium(oracle, g)
+    np.testing.assert_allclose(Sx[:40], g["Sx_sz_head"], rtol=1e-12, atol=1e-13)              # the oracle chain IS the golden chain
+    np.testing.assert_allclose(dS[:40], g["delta_S_head"], rtol=1e-9, atol=1e-12)
+    vlm.Sx_sz, vlm.delta_S = Sx, dS
+    rows = np.arange(C)[:, None]
+    for tag, psc in (("pscdef", None), ("psc1", 1)):
+        vlm.estimate_transition_prob(psc=psc, **kw)
+        assert np.array_equal(vlm.neigh_ixs, g[f"{tag}_neigh_ixs"])
+        np.testing.assert_allclose(vlm.corrcoef_compact, g[f"{tag}_corrcoef"], rtol=0, atol=5e-7)
+        np.testing.assert_allclose(vlm.corrcoef_random_compact, g[f"{tag}_corrcoef_random"], rtol=0, atol=5e-7)
+        np.testing.assert_allclose(vlm.corrcoef[rows, vlm.neigh_ixs], g[f"{tag}_corrcoef"], rtol=0, atol=5e-7)   # dense adapter
+        vlm.calculate_embedding_shift(sigma_corr=0.05, expression_scaling=True)
+        np.testing.assert_allclose(vlm.transition_prob_compact, g[f"{tag}_transition_prob"], rtol=1e-5, atol=0)   # 1e-5
+        np.testing.assert_allclose(vlm.transition_prob_random_compact, g[f"{tag}_transition_prob_random"], rtol=1e-5, atol=0)
+        np.testing.assert_allclose(vlm.transition_prob[rows, vlm.neigh_ixs], g[f"{tag}_transition_prob"], rtol=1e-5, atol=0)
+        np.testing.assert_allclose(vlm.scaling, g[f"{tag}_scaling"], rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(vlm.delta_embedding, g[f"{tag}_delta_embedding"], rtol=5e-5, atol=1e-8)
+    # ---- grid arrows from the reference's embedding displacements (the last loop iteration above = the fixture's state)
+    vlm.delta_ts, vlm.delta_ts_random = g["pscdef_delta_embedding"], g["pscdef_delta_embedding_random"]
+    vlm.estimate_transition_prob(psc=None, **kw)                                                # leaves a randomised control behind
+    vlm.calculate_grid_arrows(embed="ts", smooth=0.8, steps=(14, 11), n_neighbors=40, n_jobs=1)
+    np.testing.assert_allclose(vlm.flow_grid, g["flow_grid"], rtol=0, atol=1e-12)
+    for name in ("total_p_mass", "flow", "flow_norm", "flow_norm_magnitude", "flow_rndm", "flow_norm_rndm"):
+        np.testing.assert_allclose(getattr(vlm, name), g[name], rtol=1e-9, atol=1e-12, err_msg=name)
+
+
+def test_default_fit_is_the_exact_optimum_given_the_weights(oracle):
+    """a11 (fit_gammas default): with the oracle's OWN weight matrix handed to the kernel, the closed-form box-constrained
+    WLS must dominate SciPy's L-BFGS-B iterate on EVERY gene, and match an fp64 active-set solution of the same problem
+    to fp32 rounding.  Separately, the weights the device builds from fp32 data differ from the fp64 ones in a handful
+    of threshold cells; the effect on gamma is reported, not hidden behind a quantile."""
+    import torch
+    from velocyto_b200 import device as dev
+    G, C = 300, 500
+    S, U = synth_counts(G, C, 71)
+    rng = np.random.default_rng(72)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    X, Y = f32(S + rng.uniform(0, 1, S.shape)), f32(U + rng.uniform(0, 1, U.shape))
+    W = oracle.gamma_fit_weights("maxmin_diag", X, Y, X, Y)
+    Xd, Yd = dev.CellMajor.from_gene_major(X), dev.CellMajor.from_gene_major(Y)
+    g_dev, q_dev, _, _ = dev.fit_gammas(dev.FIT_SLOPE_WEIGHTED_OFFSET, Xd, Yd, dev.CellMajor.from_gene_major(W), lo=1e-8, hi=20.0)
+    g_dev, q_dev = g_dev.cpu().numpy().astype(np.float64), q_dev.cpu().numpy().astype(np.float64)
+    g_ref, q_ref, _ = oracle.fit_slope_weighted_offset(Y, X, W, return_R2=True)               # SciPy L-BFGS-B (estimation.py:337-366)
+    obj = lambda m, b: np.sum(W * (X * m[:, None] + b[:, None] - Y) ** 2, 1)
+    f_dev, f_ref = obj(g_dev, q_dev), obj(g_ref.astype(np.float64), q_ref.astype(np.float64))
+    live = np.isfinite(g_ref) & (W.sum(1) > 0)
+    assert np.all(f_dev[live] <= f_ref[live] * (1 + 1e-6) + 1e-9), "exact optimum must dominate the L-BFGS-B iterate on every gene"
+    # exact fp64 solution of the same box problem: interior normal equations, else the best edge
+    exact_g, exact_q = np.empty(G), np.empty(G)
+    for i in range(G):
+        w, x, y = W[i], X[i], Y[i]
+        sw, sx, sy, sxx, sxy = w.sum(), (w * x).sum(), (w * y).sum(), (w * x * x).sum(), (w * x * y).sum()
+        qmax = 2 * sy / sw
+        cands = []
+        det = sw * sxx - sx * sx
+        if det > 0:
+            m, b = (sw * sxy - sx * sy) / det, (sxx * sy - sx * sxy) / det
+            if 1e-8 <= m <= 20 and 0 <= b <= qmax:
+                cands.append((m, b))
+        for b in (0.0, qmax):
+            cands.append((min(max((sxy - b * sx) / sxx, 1e-8), 20.0), b))
+        for m in (1e-8, 20.0):
+            cands.append((m, min(max((sy - m * sx) / sw, 0.0), qmax)))
+        vals = [np.sum(w * (x * m + b - y) ** 2) for m, b in cands]
+        exact_g[i], exact_q[i] = cands[int(np.argmin(vals))]
+    np.testing.assert_allclose(g_dev[live], exact_g[live], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(q_dev[live], exact_q[live], rtol=1e-5, atol=1e-5)
+    # device-built weights (fp32 thresholds) vs the oracle's: how many cells flip, and what that does to gamma
+    Wd = dev.fit_weights("maxmin_diag", Xd, Yd, Xd, Yd)
+    flips = float((Wd.to_gene_major() != W).mean())
+    g2, _, _, _ = dev.fit_gammas(dev.FIT_SLOPE_WEIGHTED_OFFSET, Xd, Yd, Wd, lo=1e-8, hi=20.0)
+    dev_gamma = np.abs(g2.cpu().numpy()[live] - exact_g[live]) / (1e-3 + np.abs(exact_g[live]))
+    print(f"maxmin_diag weight cells differing from fp64: {flips:.2e}; max relative gamma deviation {dev_gamma.max():.2e}")
+    assert flips < 5e-4 and np.quantile(dev_gamma, 0.99) < 1e-3
+
+
+def test_fit_gammas_steady_state_with_fixperc_and_limit(oracle):
+    """steady_state cell selection combined with fixperc_q / limit_gamma: the reference slices the matrices first
+    (analysis.py:1223-1256), so the percentile constraints see the selected cells only."""
+    from velocyto_b200.analysis import VelocytoLoom
+    G, C = 60, 400
+    S, U = synth_counts(G, C, 81)
+    rng = np.random.default_rng(82)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    Sx, Ux = f32(S + rng.uniform(0, 1, S.shape)), f32(U + rng.uniform(0, 1, U.shape))
+    ss = rng.uniform(size=C) < 0.6
+    vlm = VelocytoLoom(S=S, U=U)
+    vlm.Sx_sz, vlm.Ux_sz, vlm.Sx, vlm.Ux = Sx, Ux, Sx, Ux
+    vlm.fit_gammas(steady_state_bool=ss, weighted=False, fit_offset=False, fixperc_q=True)
+    g_want, q_want = oracle.fit_slope_offset(Ux[:, ss], Sx[:, ss], fixperc_q=True)
+    np.testing.assert_allclose(vlm.q, q_want, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(vlm.gammas, g_want, rtol=0, atol=3e-5)
+    W = rng.uniform(0, 1, (G, C))
+    vlm.fit_gammas(steady_state_bool=ss, weighted=True, weights=W, fit_offset=False, limit_gamma=True)
+    g_want = oracle.fit_slope_weighted(Ux[:, ss], Sx[:, ss], W[:, ss], limit_gamma=True)
+    np.testing.assert_allclose(vlm.gammas, np.nan_to_num(g_want), rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize("metric", ["correlation", "cosine"])
+def test_device_knn_angular_metrics_match_sklearn(metric):
+    from sklearn.neighbors import NearestNeighbors
+    from velocyto_b200 import device as dev
+    from velocyto_b200.analysis import knn_distance_matrix
+    rng = np.random.default_rng(91)
+    X = rng.normal(size=(700, 12)) + rng.normal(size=(1, 12))
+    k = 15
+    idx, dist = dev.knn(X, k, include_self=False, metric=metric)
+    nn = NearestNeighbors(n_neighbors=k, metric=metric, algorithm="brute").fit(X)
+    d_ref, i_ref = nn.kneighbors()                                   # X=None: the point itself excluded
+    assert np.array_equal(idx.cpu().numpy(), i_ref)
+    np.testing.assert_allclose(dist.cpu().numpy(), d_ref, rtol=1e-9, atol=1e-13)
+    if metric == "correlation":                                      # the reference's knn_distance_matrix(metric="correlation")
+        gph = knn_distance_matrix(X, metric="correlation", k=k, mode="distance")
+        ref = nn.kneighbors_graph(X=None, mode="distance")
+        assert np.array_equal(gph.indices, ref.indices) and np.allclose(gph.data, ref.data, rtol=1e-9, atol=1e-13)
+
+
+def test_device_knn_with_many_duplicated_points():
+    """Hundreds of identical cells tie at the k-th distance: round 1 raised; now the ties are resolved by lowest index
+    and the result is still a correct kNN set (distances equal scikit-learn's, neighbours valid)."""
+    from sklearn.neighbors import NearestNeighbors
+    from velocyto_b200 import device as dev
+    rng = np.random.default_rng(93)
+    X = rng.normal(size=(900, 3))
+    X[100:500] = X[100]                                              # 400 copies of one point
+    k = 40
+    idx, dist = dev.knn(X, k, include_self=False)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    d_ref, _ = NearestNeighbors(n_neighbors=k).fit(X).kneighbors()
+    np.testing.assert_allclose(dist, d_ref, rtol=1e-12, atol=1e-15)
+    assert all(len(set(r)) == k and c not in r for c, r in enumerate(idx))
+    true_d = np.linalg.norm(X[idx] - X[:, None, :], axis=2)
+    np.testing.assert_allclose(true_d, dist, rtol=1e-12, atol=1e-15)
+    dup = idx[100:500]
+    assert np.all((dup >= 100) & (dup < 500)) and np.all(dup[150] == np.arange(100, 100 + k + 1)[np.arange(100, 100 + k + 1) != 250][:k])
+
+
+@pytest.mark.parametrize("G,C", [(37, 1003), (5, 70000)])
+def test_device_permute_rows_nsign_layouts(G, C):
+    """Unaligned rows (no TMA staging) and rows beyond the shared-memory limit (gather from L2) give the same kind of
+    result: a permutation of every gene row with random signs, deterministic in the seed."""
+    from velocyto_b200 import device as dev
+    rng = np.random.default_rng(8)
+    X = (rng.uniform(0.1, 1.0, size=(G, C)) + np.arange(C)[None, :]).astype(np.float32).astype(np.float64)
+    Xd = dev.CellMajor.from_gene_major(X)
+    Y = dev.permute_rows_nsign(Xd, 5).to_gene_major()
+    assert np.array_equal(Y, dev.permute_rows_nsign(Xd, 5).to_gene_major())
+    assert np.array_equal(np.sort(np.abs(Y), axis=1), np.sort(np.abs(X), axis=1))
+    assert 0.45 < (Y < 0).mean() < 0.55 and (np.abs(Y) == np.abs(X)).mean() < 0.01
+    assert not np.array_equal(np.abs(Y[0]), np.abs(Y[1]) - (X[1, 0] - X[0, 0]))          # rows permuted independently
+
+
+def test_velocity_threshold_matches_numpy():
+    """calculate_velocity(eps=...) threshold: eps * max over cells of the predicted U per gene (analysis.py:1377-1378)."""
+    import torch
+    from velocyto_b200 import device as dev, _cabi
+    rng = np.random.default_rng(95)
+    G, C = 333, 2100
+    S = rng.gamma(1.0, 2.0, (G, C)).astype(np.float32)
+    gam, q = rng.uniform(-0.5, 2, G).astype(np.float32), rng.uniform(-1, 1, G).astype(np.float32)
+    Sd = dev.CellMajor.from_gene_major(S.astype(np.float64))
+    thr = torch.empty(G, dtype=torch.float32, device="cuda")
+    _cabi.call("velo_dev_velocity_threshold", Sd.ptr, Sd.ld, torch.from_numpy(gam).cuda().data_ptr(),
+               torch.from_numpy(q).cuda().data_ptr(), G, C, 0.25, thr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    want = 0.25 * (gam[:, None] * S + q[:, None]).max(1)
+    np.testing.assert_allclose(thr.cpu().numpy(), want, rtol=2e-6, atol=1e-6)

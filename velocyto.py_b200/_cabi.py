@@ -83,6 +83,8 @@ PROTOTYPES = {
     "velo_dev_sample_neighbors": (_int, [_ptr, _i64, _int, _ptr, _int, C.c_uint64, _ptr, _ptr, _ptr]),
     "velo_dev_permute_rows_nsign": (_int, [_ptr, _ptr, _i64, _i64, _i64, C.c_uint64, _ptr]),
     "velo_dev_knn": (_int, [_ptr, _i64, _int, _int, _int, _ptr, _ptr, _ptr]),
+    "velo_dev_knn_query": (_int, [_ptr, _i64, _int, _ptr, _i64, _int, _ptr, _ptr, _ptr]),
+    "velo_dev_grid_flow": (_int, [_ptr, _ptr, _i64, _int, _ptr, _int, _dbl, _ptr, _ptr, _ptr]),
     "velo_dev_knn_range": (_int, [_ptr, _i64, _int, _int, _int, _i64, _i64, _ptr, _ptr, _ptr]),
 }
 

@@ -251,6 +251,15 @@ class VelocytoLoom:
                 borrow = {"use_S_size" if name == "U" else "use_Sx_size": use_S_size_for_U}
                 getattr(self, "_normalize_" + name)(target_size=target_size[1], **borrow, **common)
 
+    # ------------------------------------------------------------------ perform_PCA (analysis.py:678-702)
+    def perform_PCA(self, which: str = "S_norm", n_components: int = None, div_by_std: bool = False) -> None:
+        """PCA with cells as samples; creates ``pca`` (the fitted attributes scikit-learn's object would carry) and
+        ``pcs`` ``(cells, npcs)``.  Exact (eigendecomposition of the fp64 second-moment matrix accumulated on the
+        device) where scikit-learn's ``svd_solver="auto"`` switches to a randomised solver for large inputs."""
+        from . import device as dev
+        pcs, self.pca = dev.pca(self._dev(which), n_components, div_by_std)
+        self.pcs = pcs.cpu().numpy()
+
     # ------------------------------------------------------------------ knn_imputation (analysis.py:933-1023)
     def knn_imputation(self, k: int = None, pca_space: float = True, metric: str = "euclidean", diag: float = 1,
                        n_pca_dims: int = None, maximum: bool = False, size_norm: bool = True,
@@ -663,6 +672,46 @@ class VelocytoLoom:
                 setattr(self, "scaling_rndm" if rnd else "scaling", sc)
                 de = de * sc[:, None]
             setattr(self, "delta_embedding_random" if rnd else "delta_embedding", de)
+
+
+    # ------------------------------------------------------------------ calculate_grid_arrows (analysis.py:1735-1816)
+    def calculate_grid_arrows(self, embed: str = "embedding", smooth: float = 0.5, steps: Tuple = (40, 40),
+                              n_neighbors: int = 100, n_jobs: int = 4) -> None:
+        """Velocity field on a regular grid: gaussian-kernel average of ``delta_<embed>`` over the ``n_neighbors``
+        cells nearest to every grid point.  Creates ``flow_embedding``, ``flow_grid``, ``flow``, ``flow_norm``,
+        ``flow_norm_magnitude``, ``total_p_mass`` (and the ``_rndm`` twins when a randomised control exists)."""
+        from . import device as dev
+        embedding = np.asarray(getattr(self, embed))
+        if not hasattr(self, f"delta_{embed}"):
+            raise KeyError("This embedding does not have a delta_*")
+        delta_embedding = getattr(self, f"delta_{embed}")
+        has_random = hasattr(self, "corrcoef_random") or hasattr(self, "_corrcoef_random_dev")
+        grs = []
+        for dim_i in range(embedding.shape[1]):                                          # analysis.py:1776-1782
+            m, M = np.min(embedding[:, dim_i]), np.max(embedding[:, dim_i])
+            m = m - 0.025 * np.abs(M - m)
+            M = M + 0.025 * np.abs(M - m)                                                # (uses the widened m, as the reference does)
+            grs.append(np.linspace(m, M, steps[dim_i]))
+        meshes_tuple = np.meshgrid(*grs)
+        gridpoints_coordinates = np.vstack([i.flat for i in meshes_tuple]).T
+        neighs, dists = dev.knn_query(embedding, gridpoints_coordinates, n_neighbors)    # analysis.py:1788-1790
+        std = np.mean([(g[1] - g[0]) for g in grs])
+        mass, UZ = dev.grid_flow(neighs, dists, delta_embedding, smooth * std)           # analysis.py:1792-1797
+        self.total_p_mass = mass.cpu().numpy()
+        UZ = UZ.cpu().numpy()
+        magnitude = np.linalg.norm(UZ, axis=1)
+        self.flow_embedding = embedding
+        self.flow_grid = gridpoints_coordinates
+        self.flow = UZ
+        self.flow_norm = UZ / np.percentile(magnitude, 99.5)
+        self.flow_norm_magnitude = np.linalg.norm(self.flow_norm, axis=1)
+        if has_random:                                                                   # analysis.py:1809-1816
+            _, UZ_rndm = dev.grid_flow(neighs, dists, getattr(self, f"delta_{embed}_random"), smooth * std)
+            UZ_rndm = UZ_rndm.cpu().numpy()
+            magnitude_rndm = np.linalg.norm(UZ, axis=1)                                  # (of UZ, as in the reference)
+            self.flow_rndm = UZ_rndm
+            self.flow_norm_rndm = UZ_rndm / np.percentile(magnitude_rndm, 99.5)
+            self.flow_norm_magnitude_rndm = np.linalg.norm(self.flow_norm_rndm, axis=1)
 
 
 for _n in _MATRIX_ATTRS:

@@ -263,9 +263,49 @@ __global__ void __launch_bounds__(256) k_embedding_shift(const float *__restrict
     }
 }
 
+// calculate_grid_arrows (analysis.py:1794-1803): one warp per grid point.  w = N(0, sigma).pdf(dist) over the point's
+// n_neighbors nearest cells, mass = sum w, flow = sum w * delta[neigh] / max(1, mass).  fp64 like the reference.
+__global__ void __launch_bounds__(256) k_grid_flow(const int32_t *__restrict__ neighs, const double *__restrict__ dists,
+                                                   int64_t npts, int k, const double *__restrict__ delta, int dims,
+                                                   double sigma, double *__restrict__ mass, double *__restrict__ flow)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= npts) return;
+    const double norm = 1.0 / (sigma * 2.5066282746310002);       // 1 / (sigma * sqrt(2 pi)): scipy.stats.norm.pdf
+    double ms = 0.0;
+    for (int n = lane; n < k; n += 32) {
+        const double z = dists[p * k + n] / sigma;
+        ms += exp(-0.5 * z * z) * norm;
+    }
+    ms = warp_sum(ms);
+    const double inv = 1.0 / fmax(1.0, ms);
+    for (int d = 0; d < dims; ++d) {
+        double a = 0.0;
+        for (int n = lane; n < k; n += 32) {
+            const double z = dists[p * k + n] / sigma;
+            a += exp(-0.5 * z * z) * norm * delta[static_cast<int64_t>(neighs[p * k + n]) * dims + d];
+        }
+        a = warp_sum(a);
+        if (lane == 0) flow[p * dims + d] = a * inv;
+    }
+    if (lane == 0) mass[p] = ms;
+}
+
 }  // namespace velo
 
 using namespace velo;
+
+extern "C" int velo_dev_grid_flow(const int32_t *neighs, const double *dists, int64_t npts, int k, const double *delta,
+                                  int dims, double sigma, double *mass, double *flow, velo_stream_t stream)
+{
+    VELO_REQUIRE(neighs && dists && delta && mass && flow && npts >= 0 && k > 0 && dims > 0 && sigma > 0, "grid_flow: bad arguments");
+    if (npts == 0) return VELO_OK;
+    k_grid_flow<<<static_cast<unsigned>((npts + 7) / 8), 256, 0, as_stream(stream)>>>(neighs, dists, npts, k, delta, dims, sigma,
+                                                                                    mass, flow);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
 
 extern "C" int velo_dev_delta_transform(const float *delta_S_cm, float *out_cm, int64_t ld, int64_t C, double dt,
                                         int transform, double psc, velo_stream_t stream)

@@ -21,6 +21,7 @@ __device__ __forceinline__ uint32_t knn_f2key(float f)   // f >= 0
 
 struct KnnParams {
     const double *X;       // C x D
+    const double *Q;       // query points (nq x D) when they are not points of X, else nullptr
     int64_t C, q0, nq;     // points; query range [q0, q0 + nq)
     int D, k, include_self, P;
     int32_t *out_idx;      // C x k
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
     for (int64_t q = p.q0 + blockIdx.x; q < p.q0 + p.nq; q += gridDim.x) {
-        for (int d = tid; d < p.D; d += nt) xq[d] = p.X[q * p.D + d];
+        for (int d = tid; d < p.D; d += nt) xq[d] = p.Q ? p.Q[(q - p.q0) * p.D + d] : p.X[q * p.D + d];
         __syncthreads();
         // 1. distances -> keys
         for (int64_t j = tid; j < p.C; j += nt) {
@@ -201,11 +202,27 @@ extern "C" int velo_dev_knn(const double *X, int64_t C, int D, int k, int includ
     return velo_dev_knn_range(X, C, D, k, include_self, 0, C, out_idx, out_dist, stream);
 }
 
+static int knn_launch(const double *X, const double *Q, int64_t C, int D, int k, int include_self, int64_t q0, int64_t nq,
+                      int32_t *out_idx, double *out_dist, velo_stream_t stream);
+
 extern "C" int velo_dev_knn_range(const double *X, int64_t C, int D, int k, int include_self, int64_t q0, int64_t nq,
                                   int32_t *out_idx, double *out_dist, velo_stream_t stream)
 {
-    VELO_REQUIRE(X && out_idx && C > 0 && D > 0 && D <= 4096, "knn: bad arguments");
     VELO_REQUIRE(q0 >= 0 && nq >= 0 && q0 + nq <= C, "knn: query range outside [0, %lld)", static_cast<long long>(C));
+    return knn_launch(X, nullptr, C, D, k, include_self, q0, nq, out_idx, out_dist, stream);
+}
+
+extern "C" int velo_dev_knn_query(const double *X, int64_t C, int D, const double *Q, int64_t nq, int k,
+                                  int32_t *out_idx, double *out_dist, velo_stream_t stream)
+{
+    VELO_REQUIRE(Q && nq >= 0, "knn_query: bad arguments");
+    return knn_launch(X, Q, C, D, k, 1, 0, nq, out_idx, out_dist, stream);
+}
+
+static int knn_launch(const double *X, const double *Q, int64_t C, int D, int k, int include_self, int64_t q0, int64_t nq,
+                      int32_t *out_idx, double *out_dist, velo_stream_t stream)
+{
+    VELO_REQUIRE(X && out_idx && C > 0 && D > 0 && D <= 4096, "knn: bad arguments");
     if (nq == 0) return VELO_OK;
     VELO_REQUIRE(k > 0 && k <= (include_self ? C : C - 1), "knn: k = %d out of range for %lld points", k,
                  static_cast<long long>(C));
@@ -229,7 +246,7 @@ extern "C" int velo_dev_knn_range(const double *X, int64_t C, int D, int k, int 
     VELO_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&overflow), sizeof(int), st));
     VELO_CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int), st));
     KnnParams p;
-    p.X = X; p.C = C; p.q0 = q0; p.nq = nq; p.D = D; p.k = k; p.include_self = include_self; p.P = P;
+    p.X = X; p.Q = Q; p.C = C; p.q0 = q0; p.nq = nq; p.D = D; p.k = k; p.include_self = include_self; p.P = P;
     p.out_idx = out_idx; p.out_dist = out_dist; p.scratch = scratch; p.overflow = overflow;
     k_knn_bruteforce<<<static_cast<unsigned>(grid), 512, smem, st>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);

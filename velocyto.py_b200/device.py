@@ -461,6 +461,104 @@ def knn(points, k: int, include_self: bool = False, metric: str = "euclidean", q
     return idx, dist
 
 
+def knn_query(points, queries, k: int):
+    """The k nearest ``points`` (C x D) of every row of ``queries`` (nq x D), Euclidean, ascending -- what
+    ``NearestNeighbors().fit(points).kneighbors(queries)`` returns (calculate_grid_arrows, analysis.py:1788-1790).
+    Returns ``(idx int32 (nq, k), dist float64 (nq, k))`` CUDA tensors."""
+    device = require_cuda()
+    as_t = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))).to(
+        device=device, dtype=torch.float64).contiguous()
+    X, Q = as_t(points), as_t(queries)
+    assert X.shape[1] == Q.shape[1]
+    idx = torch.empty((Q.shape[0], k), dtype=torch.int32, device=device)
+    dist = torch.empty((Q.shape[0], k), dtype=torch.float64, device=device)
+    _cabi.call("velo_dev_knn_query", X.data_ptr(), X.shape[0], X.shape[1], Q.data_ptr(), Q.shape[0], int(k), idx.data_ptr(),
+               dist.data_ptr(), _stream_ptr())
+    return idx, dist
+
+
+def grid_flow(neighs: torch.Tensor, dists: torch.Tensor, delta, sigma: float):
+    """Gaussian-kernel average of the cells' embedding displacements around every grid point
+    (analysis.py:1792-1797): returns ``(total_p_mass (npts,), flow (npts, dims))`` float64 CUDA tensors."""
+    delta = torch.as_tensor(np.ascontiguousarray(delta, dtype=np.float64)).to(neighs.device)
+    npts, k = neighs.shape
+    mass = torch.empty(npts, dtype=torch.float64, device=neighs.device)
+    flow = torch.empty((npts, delta.shape[1]), dtype=torch.float64, device=neighs.device)
+    _cabi.call("velo_dev_grid_flow", neighs.data_ptr(), dists.data_ptr(), npts, k, delta.data_ptr(), delta.shape[1],
+               float(sigma), mass.data_ptr(), flow.data_ptr(), _stream_ptr())
+    return mass, flow
+
+
+# --------------------------------------------------------------------------- PCA (analysis.py:678-702)
+class PCAResult:
+    """The attributes of ``sklearn.decomposition.PCA`` that velocyto reads after ``perform_PCA`` (``explained_variance_ratio_``
+    for choosing ``n_pca_dims``, doc/tutorial/analysis.rst:118-121; ``components_`` / ``mean_`` for projections)."""
+
+    def __init__(self, components, explained_variance, explained_variance_ratio, singular_values, mean, n_samples):
+        self.components_, self.explained_variance_ = components, explained_variance
+        self.explained_variance_ratio_, self.singular_values_, self.mean_ = explained_variance_ratio, singular_values, mean
+        self.n_components_, self.n_features_in_, self.n_samples_ = components.shape[0], components.shape[1], n_samples
+
+    def transform(self, X):
+        return (np.asarray(X) - self.mean_) @ self.components_.T
+
+
+def pca(X: CellMajor, n_components: Optional[int] = None, div_by_std: bool = False, block: int = 8192):
+    """Exact PCA of the cells (rows = samples, genes = features) as ``PCA(n_components).fit_transform(X.T)`` computes it
+    (analysis.py:697-702): features centred, components = leading right singular vectors with scikit-learn's sign rule
+    (largest-magnitude loading positive), ``pcs = U * S``.
+
+    The matrix stays on the device: fp64 second moments accumulated over cell blocks -- the gene x gene covariance,
+    or the cell x cell Gram matrix when there are fewer cells than genes -- one symmetric eigendecomposition
+    (cuSOLVER through ``torch.linalg.eigh``: a plain library call, PCA is not part of the hand-written hot path), and
+    a projection GEMM.  Returns ``(pcs (C, n) float64 CUDA, PCAResult)``."""
+    C, G, dv = X.C, X.G, X.t.device
+    n = min(C, G) if n_components is None else int(n_components)
+    if not 0 < n <= min(C, G):
+        raise ValueError(f"n_components={n_components} must be between 1 and min(n_samples, n_features)={min(C, G)}")
+
+    def rows(r0):                                   # one block of samples in fp64 (optionally scaled by 1 / per-cell std)
+        Xb = X.t[r0:r0 + block, :G].double()
+        if div_by_std:
+            Xb = Xb / Xb.std(dim=1, unbiased=False, keepdim=True)            # X.T / X.std(0)   (analysis.py:700)
+        return Xb
+
+    mean = torch.zeros(G, dtype=torch.float64, device=dv)
+    for r0 in range(0, C, block):
+        mean += rows(r0).sum(0)
+    mean /= C
+    if G <= C:                                      # covariance route: G x G
+        M = torch.zeros((G, G), dtype=torch.float64, device=dv)
+        for r0 in range(0, C, block):
+            Xb = rows(r0) - mean
+            M.addmm_(Xb.t(), Xb)
+        lam, V = torch.linalg.eigh(M)
+        lam, V = lam.flip(0)[:n].clamp_min(0), V.flip(1)[:, :n]                # descending
+        comps = V.t().contiguous()                                              # (n, G)
+    else:                                           # Gram route: C x C, components = X_c^T u / s
+        Xc = torch.cat([rows(r0) - mean for r0 in range(0, C, block)])
+        lam, Uv = torch.linalg.eigh(Xc @ Xc.t())
+        lam, Uv = lam.flip(0)[:n].clamp_min(0), Uv.flip(1)[:, :n]
+        comps = (Xc.t() @ Uv / lam.sqrt().clamp_min(1e-300)).t().contiguous()
+        comps = comps / torch.linalg.vector_norm(comps, dim=1, keepdim=True).clamp_min(1e-300)
+        del Xc
+    # scikit-learn's svd_flip(u_based_decision=False): the largest-magnitude loading of every component is positive
+    piv = comps.abs().argmax(dim=1)
+    sign = torch.sign(comps[torch.arange(n, device=dv), piv])
+    sign[sign == 0] = 1
+    comps = comps * sign[:, None]
+    pcs = torch.empty((C, n), dtype=torch.float64, device=dv)
+    total_var = torch.zeros((), dtype=torch.float64, device=dv)
+    for r0 in range(0, C, block):
+        Xb = rows(r0) - mean
+        pcs[r0:r0 + block] = Xb @ comps.t()
+        total_var += (Xb * Xb).sum()
+    ev = lam / (C - 1)
+    res = PCAResult(comps.cpu().numpy(), ev.cpu().numpy(), (ev / (total_var / (C - 1))).cpu().numpy(),
+                    lam.sqrt().cpu().numpy(), mean.cpu().numpy(), C)
+    return pcs, res
+
+
 # --------------------------------------------------------------------------- device-side randomisation (opt-in)
 def sample_neighbors(knn_idx: torch.Tensor, p, m: int, seed: int):
     """Weighted sampling without replacement of ``m`` of the ``W`` candidates of every cell on the device
