@@ -315,6 +315,18 @@ int velo_dev_knn_smooth_csr(const int64_t *w_indptr, const int32_t *w_indices, c
                             float *out_cm, int64_t ld_out, int64_t C, int64_t g0, int64_t ng, int maximum,
                             velo_stream_t stream);
 
+/* Sparse ingest: counts arrive as CSR by cell -- what 10x / AnnData / sparse-loom HDF5 files store
+ * (indptr over cells, gene ids, values) -- and never exist as a dense float64 host matrix (the reference's loader,
+ * analysis.py:56-64, reads `ds.layer[...][:, :]` densely: 120 GB per matrix at 500k x 30k).
+ * velo_dev_csr_to_cellmajor: dense cell-major fp32 slab [g0, g0 + ng) of the matrix: out_cm[c * ld + (g - g0)]
+ * (pad columns zeroed).  Gene ids sorted within a cell.
+ * velo_dev_csr_cell_sums_scale: optional in-place values[q] *= factor[cell] (non-finite -> 0), then optional per-cell
+ * totals (fp64) of the (rescaled) values: the size normalisation of analysis.py:535-584 on the sparse form. */
+int velo_dev_csr_to_cellmajor(const int64_t *indptr, const int32_t *genes, const float *values, int64_t C,
+                              int64_t g0, int64_t ng, float *out_cm, int64_t ld, velo_stream_t stream);
+int velo_dev_csr_cell_sums_scale(const int64_t *indptr, float *values, int64_t C, const double *factor,
+                                 double *sums, velo_stream_t stream);
+
 /* Exact brute-force kNN (Euclidean) in a low-dimensional space: X is C x D fp64 row-major (device); writes the k
  * nearest points of every point in ascending distance: out_idx (C x k int32), out_dist (C x k fp64 or NULL).
  * include_self = 0 excludes the query point itself (scikit-learn's kneighbors with X=None, neighbors.py:370-376,

@@ -837,3 +837,40 @@ def test_velocity_threshold_matches_numpy():
                torch.from_numpy(q).cuda().data_ptr(), G, C, 0.25, thr.data_ptr(), torch.cuda.current_stream().cuda_stream)
     want = 0.25 * (gam[:, None] * S + q[:, None]).max(1)
     np.testing.assert_allclose(thr.cpu().numpy(), want, rtol=2e-6, atol=1e-6)
+
+
+def test_sparse_ingest_matches_dense_path():
+    """Counts handed over as SciPy sparse / (data, indices, indptr) triplets go to the device as CSR by cell and are
+    densified THERE: every downstream result equals the dense-host path bit for bit, and no dense host matrix exists."""
+    import torch
+    from velocyto_b200 import device as dev
+    from velocyto_b200.analysis import VelocytoLoom
+    G, C = 513, 301
+    S, U = synth_counts(G, C, 97)
+    S[:, 17] = 0                                                   # an empty cell
+    Ssp, Usp = sparse.csr_matrix(S), sparse.coo_matrix(U)          # any SciPy format is accepted
+    csr = dev.CsrCounts.from_scipy(Ssp)
+    assert csr.C == C and csr.G == G and csr.nnz == int((S != 0).sum())
+    np.testing.assert_array_equal(csr.cell_sums().cpu().numpy(), S.sum(0))
+    np.testing.assert_array_equal(csr.to_cellmajor().to_gene_major(), S)
+    np.testing.assert_array_equal(csr.to_cellmajor(96, 200).to_gene_major(), S[96:296])            # a gene slab
+    fac = torch.from_numpy(1.0 / np.maximum(S.sum(0), 1)).cuda()
+    np.testing.assert_allclose(csr.scaled(fac).to_cellmajor().to_gene_major(), S / np.maximum(S.sum(0), 1), rtol=1e-7)
+    dense, sp = VelocytoLoom(S=S, U=U), VelocytoLoom(S=Ssp, U=Usp)
+    cs = sparse.csc_matrix(S)
+    tri = VelocytoLoom.from_csr((cs.data, cs.indices, cs.indptr), (sparse.csc_matrix(U).data, sparse.csc_matrix(U).indices,
+                                                                  sparse.csc_matrix(U).indptr), n_genes=G)
+    for v in (dense, sp, tri):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            v.normalize("both", size=True, log=True)
+        v.perform_PCA(n_components=8)
+        v.knn_imputation(k=12, n_pca_dims=6)
+        v.fit_gammas(weighted=False, fit_offset=True)
+    assert sparse.issparse(sp.S) and sparse.issparse(tri.U)
+    for name in ("S_sz", "U_norm", "Sx_sz", "Ux_sz"):
+        np.testing.assert_array_equal(getattr(sp, name), getattr(dense, name), err_msg=name)
+        np.testing.assert_array_equal(getattr(tri, name), getattr(dense, name), err_msg=name)
+    np.testing.assert_array_equal(sp.gammas, dense.gammas)
+    np.testing.assert_array_equal(sp.initial_cell_size, dense.initial_cell_size)

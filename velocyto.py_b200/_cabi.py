@@ -80,6 +80,8 @@ PROTOTYPES = {
     "velo_dev_size_normalize": (_int, [_ptr, _i64, _i64, _i64, _ptr, _dbl, _int, _ptr, _ptr, _ptr]),
     "velo_dev_knn_smooth": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr]),
     "velo_dev_knn_smooth_csr": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _ptr]),
+    "velo_dev_csr_to_cellmajor": (_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr]),
+    "velo_dev_csr_cell_sums_scale": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "velo_dev_sample_neighbors": (_int, [_ptr, _i64, _int, _ptr, _int, C.c_uint64, _ptr, _ptr, _ptr]),
     "velo_dev_permute_rows_nsign": (_int, [_ptr, _ptr, _i64, _i64, _i64, C.c_uint64, _ptr]),
     "velo_dev_knn": (_int, [_ptr, _i64, _int, _int, _int, _ptr, _ptr, _ptr]),

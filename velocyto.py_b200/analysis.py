@@ -70,6 +70,45 @@ class _DeviceBacked:
         obj.__dict__.setdefault("_devs", {}).pop(self.name, None)
 
 
+class _LazyDense:
+    """Descriptor for the reference's dense ``(cells, cells)`` float64 results (``corrcoef``, ``transition_prob`` and
+    their ``_random`` twins).  The native result is the compact ``(cells, m)`` device matrix aligned with ``neigh_ixs``;
+    the dense form (800 MB per matrix at 10k cells, most of a second of scatter + D2H + host allocation each) is built
+    the first time it is READ, and only when cells <= ``dense_limit`` -- a pipeline that goes on to
+    ``calculate_embedding_shift`` / ``calculate_grid_arrows`` never pays for it."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __get__(self, obj, owner=None):
+        if obj is None:
+            return self
+        cache = obj.__dict__.setdefault("_dense", {})
+        if self.name in cache:
+            return cache[self.name]
+        src = obj.__dict__.get("_dense_src", {}).get(self.name)
+        if src is None:
+            raise AttributeError(f"'{type(obj).__name__}' object has no attribute '{self.name}'")
+        compact, ix, C, limit = src
+        if C > limit:
+            raise AttributeError(f"{self.name}: the dense ({C} x {C}) matrix is not materialised above dense_limit={limit} "
+                                 f"cells; use {self.name}_compact with neigh_ixs")
+        from . import device as dev
+        cache[self.name] = dev.scatter_dense(compact, ix, C).cpu().numpy()
+        return cache[self.name]
+
+    def __set__(self, obj, value):
+        obj.__dict__.setdefault("_dense", {})[self.name] = value
+        obj.__dict__.setdefault("_dense_src", {}).pop(self.name, None)
+
+    def __delete__(self, obj):
+        obj.__dict__.setdefault("_dense", {}).pop(self.name, None)
+        obj.__dict__.setdefault("_dense_src", {}).pop(self.name, None)
+
+
+_DENSE_ATTRS = ("corrcoef", "corrcoef_random", "transition_prob", "transition_prob_random")
+
+
 def knn_graph_device(data: np.ndarray, k: int, mode: str = "connectivity", include_self: bool = False,
                      metric: str = "euclidean") -> sparse.csr_matrix:
     """kNN graph built by the brute-force device kernel (``velo_dev_knn``): the CSR scikit-learn's
@@ -128,11 +167,29 @@ class VelocytoLoom:
             raise NotImplementedError("loom I/O is out of scope (SURVEY.md section 2): pass the S and U count matrices")
         if S is None or U is None:
             raise ValueError("S and U (genes x cells) are required")
-        self.S, self.U = np.asarray(S, dtype=np.float64), np.asarray(U, dtype=np.float64)
-        self.A = np.zeros_like(self.S) if A is None else np.asarray(A)
+        # SciPy sparse count matrices stay sparse on the host and go to the device as CSR by cell (device.CsrCounts);
+        # the reference's loader materialises dense float64 matrices (analysis.py:56-64: 24 GB per layer at 100k x 30k)
+        keep = lambda M: sparse.csc_matrix(M, dtype=np.float64) if sparse.issparse(M) else np.asarray(M, dtype=np.float64)
+        self.S, self.U = keep(S), keep(U)
+        if A is None:
+            self.A = sparse.csc_matrix(self.S.shape) if sparse.issparse(self.S) else np.zeros_like(self.S)
+        else:
+            self.A = A if sparse.issparse(A) else np.asarray(A)
         self.ca, self.ra = dict(ca or {}), dict(ra or {})
-        self.initial_cell_size = self.S.sum(0)                 # analysis.py:62-63
-        self.initial_Ucell_size = self.U.sum(0)
+        self.initial_cell_size = np.asarray(self.S.sum(0)).ravel()        # analysis.py:62-63
+        self.initial_Ucell_size = np.asarray(self.U.sum(0)).ravel()
+
+    @classmethod
+    def from_csr(cls, S: Tuple, U: Tuple, n_genes: int, A: Tuple = None, ca: Optional[Dict] = None,
+                 ra: Optional[Dict] = None) -> "VelocytoLoom":
+        """Build the object from by-cell compressed layers, ``(data, indices, indptr)`` per layer with ``indptr`` over
+        CELLS and gene ids as indices -- the arrays a 10x / AnnData / sparse-loom HDF5 file stores, read with any HDF5
+        reader (h5py is not part of this package's requirements).  Nothing dense is built on the host."""
+        def mat(t):
+            data, indices, indptr = t
+            return sparse.csc_matrix((np.asarray(data, dtype=np.float64), np.asarray(indices), np.asarray(indptr)),
+                                     shape=(n_genes, len(indptr) - 1))
+        return cls(S=mat(S), U=mat(U), A=None if A is None else mat(A), ca=ca, ra=ra)
 
     # ------------------------------------------------------------------ device residency helpers
     def _dev(self, name: str, residual: bool = False):
@@ -143,12 +200,18 @@ class VelocytoLoom:
         from . import device as dev
         devs = self.__dict__.setdefault("_devs", {})
         host = self.__dict__.setdefault("_host", {})
-        need_split = (residual and name in host and getattr(host[name], "dtype", None) == np.float64
+        need_split = (residual and name in host and not sparse.issparse(host[name])
+                      and getattr(host[name], "dtype", None) == np.float64
                       and (name not in devs or devs[name].lo is None)
                       and name not in self.__dict__.setdefault("_fp32_exact", set()))
         if name not in devs or need_split:
             if name not in host:
                 raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+            if sparse.issparse(host[name]):
+                # sparse host layer: 8 bytes per NON-ZERO over PCIe, densified on the device (fp32, cell-major)
+                devs[name] = dev.CsrCounts.from_scipy(host[name]).to_cellmajor()
+                self.__dict__["_fp32_exact"].discard(name)
+                return devs[name]
             devs[name] = dev.CellMajor.from_gene_major(host[name], residual=residual)
             if residual and devs[name].lo is None:
                 self.__dict__["_fp32_exact"].add(name)
@@ -497,8 +560,12 @@ class VelocytoLoom:
         random_backend = kwargs.pop("random_backend", "reference")
         if random_backend not in ("reference", "device"):
             raise ValueError("random_backend must be 'reference' or 'device'")
-        for stale in ("_corrcoef_random_dev", "corrcoef_random", "corrcoef_random_compact"):
+        for stale in ("_corrcoef_random_dev", "corrcoef_random_compact", "_transition_prob_random_dev",
+                      "transition_prob_random_compact"):
             self.__dict__.pop(stale, None)
+        for stale in ("corrcoef_random", "transition_prob_random"):
+            if stale in self.__dict__.get("_dense", {}) or stale in self.__dict__.get("_dense_src", {}):
+                delattr(self, stale)
         _numba_seed(random_seed)                                                         # analysis.py:1501
         self.which_hidim = hidim
         if "n_neighbors" in kwargs:
@@ -613,10 +680,12 @@ class VelocytoLoom:
                             "it is probably a small isolated cluster converging after imputation.")
         setattr(self, "_" + name + "_dev", corr)
         setattr(self, name + "_compact", corr.cpu().numpy())
-        if C <= dense_limit:
-            setattr(self, name, dev.scatter_dense(corr, ix, C).cpu().numpy())
-        elif hasattr(self, name):
-            delattr(self, name)
+        self._set_dense_source(name, corr, ix, C, dense_limit)
+
+    def _set_dense_source(self, name: str, compact, ix, C: int, dense_limit: int) -> None:
+        """Register the compact device result behind the lazily built dense attribute ``name`` (see _LazyDense)."""
+        self.__dict__.setdefault("_dense", {}).pop(name, None)
+        self.__dict__.setdefault("_dense_src", {})[name] = (compact, ix, C, dense_limit)
 
     # ------------------------------------------------------------------ calculate_embedding_shift (analysis.py:1670-1733)
     def calculate_embedding_shift(self, sigma_corr: float = 0.05, expression_scaling: bool = True,
@@ -659,8 +728,7 @@ class VelocytoLoom:
                 tp[poisoned] = float("nan")
             setattr(self, "_" + pname + "_dev", tp)
             setattr(self, pname + "_compact", tp.cpu().numpy())
-            if C <= dense_limit:
-                setattr(self, pname, dev.scatter_dense(tp, ix_m, C).cpu().numpy())
+            self._set_dense_source(pname, tp, ix_m, C, dense_limit)
         # delta_embedding = sum_j (P_ij - 1/k) * unit(emb_j - emb_i), neighbours only (analysis.py:1704-1712)
         for cname, pname in names:
             tp = getattr(self, "_" + pname + "_dev")
@@ -685,7 +753,7 @@ class VelocytoLoom:
         if not hasattr(self, f"delta_{embed}"):
             raise KeyError("This embedding does not have a delta_*")
         delta_embedding = getattr(self, f"delta_{embed}")
-        has_random = hasattr(self, "corrcoef_random") or hasattr(self, "_corrcoef_random_dev")
+        has_random = "_corrcoef_random_dev" in self.__dict__ or "corrcoef_random" in self.__dict__.get("_dense", {})
         grs = []
         for dim_i in range(embedding.shape[1]):                                          # analysis.py:1776-1782
             m, M = np.min(embedding[:, dim_i]), np.max(embedding[:, dim_i])
@@ -716,6 +784,8 @@ class VelocytoLoom:
 
 for _n in _MATRIX_ATTRS:
     setattr(VelocytoLoom, _n, _DeviceBacked(_n))
+for _n in _DENSE_ATTRS:
+    setattr(VelocytoLoom, _n, _LazyDense(_n))
 
 
 # --------------------------------------------------------------------------- host RNG helpers (analysis.py:2407-2420)

@@ -70,9 +70,75 @@ __global__ void __launch_bounds__(256) k_knn_smooth_csr(const int64_t *__restric
     }
 }
 
+// CSR by cell -> dense cell-major slab [g0, g0 + ng): one warp per cell; the row is zero-filled with 128-bit stores,
+// then the cell's entries inside the slab are scattered (sorted gene ids: binary search for the sub-range).
+__global__ void __launch_bounds__(256) k_csr_to_cellmajor(const int64_t *__restrict__ indptr, const int32_t *__restrict__ genes,
+                                                          const float *__restrict__ values, int64_t C, int64_t g0, int64_t ng,
+                                                          float *__restrict__ out, int64_t ld)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    float4 *row4 = reinterpret_cast<float4 *>(out + c * ld);
+    for (int64_t q = lane; q < (ld >> 2); q += 32) row4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    const int64_t r0 = indptr[c], r1 = indptr[c + 1];
+    const int64_t a = lower_bound_i32(genes, r0, r1, static_cast<int32_t>(g0));
+    const int64_t b = lower_bound_i32(genes, a, r1, static_cast<int32_t>(g0 + ng));
+    for (int64_t q = a + lane; q < b; q += 32) out[c * ld + (genes[q] - g0)] = values[q];
+}
+
+// per-cell totals of a CSR-by-cell matrix (= X.sum(0) of the reference's genes x cells matrix), fp64; optional
+// in-place rescaling values[q] *= factor[cell] (size normalisation keeps the sparsity pattern)
+__global__ void __launch_bounds__(256) k_csr_cell_sums_scale(const int64_t *__restrict__ indptr, float *__restrict__ values,
+                                                             int64_t C, const double *__restrict__ factor,
+                                                             double *__restrict__ sums)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int64_t r0 = indptr[c], r1 = indptr[c + 1];
+    if (factor) {
+        const double f = factor[c];
+        for (int64_t q = r0 + lane; q < r1; q += 32) {
+            const double y = f * static_cast<double>(values[q]);
+            values[q] = isfinite(y) ? static_cast<float>(y) : 0.f;
+        }
+    }
+    if (sums) {
+        double s = 0.0;
+        for (int64_t q = r0 + lane; q < r1; q += 32) s += static_cast<double>(values[q]);
+        s = warp_sum(s);
+        if (lane == 0) sums[c] = s;
+    }
+}
+
 }  // namespace velo
 
 using namespace velo;
+
+extern "C" int velo_dev_csr_to_cellmajor(const int64_t *indptr, const int32_t *genes, const float *values, int64_t C,
+                                         int64_t g0, int64_t ng, float *out_cm, int64_t ld, velo_stream_t stream)
+{
+    VELO_REQUIRE(indptr && genes && values && out_cm && C >= 0 && g0 >= 0 && ng > 0 && ld >= ng && (ld % 4) == 0,
+                 "csr_to_cellmajor: bad arguments");
+    VELO_REQUIRE((reinterpret_cast<uintptr_t>(out_cm) & 15) == 0, "csr_to_cellmajor: out_cm must be 16-byte aligned");
+    if (C == 0) return VELO_OK;
+    k_csr_to_cellmajor<<<static_cast<unsigned>((C + 7) / 8), 256, 0, as_stream(stream)>>>(indptr, genes, values, C, g0, ng,
+                                                                                        out_cm, ld);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
+
+extern "C" int velo_dev_csr_cell_sums_scale(const int64_t *indptr, float *values, int64_t C, const double *factor,
+                                            double *sums, velo_stream_t stream)
+{
+    VELO_REQUIRE(indptr && values && C >= 0 && (factor || sums), "csr_cell_sums_scale: bad arguments");
+    if (C == 0) return VELO_OK;
+    k_csr_cell_sums_scale<<<static_cast<unsigned>((C + 7) / 8), 256, 0, as_stream(stream)>>>(indptr, values, C, factor, sums);
+    VELO_LAUNCH_CHECK();
+    return VELO_OK;
+}
 
 extern "C" int velo_dev_knn_smooth_csr(const int64_t *w_indptr, const int32_t *w_indices, const float *w_weights,
                                        const int64_t *s_indptr, const int32_t *s_genes, const float *s_values,

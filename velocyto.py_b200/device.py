@@ -426,6 +426,66 @@ def knn_smooth_csr(w_indptr, w_indices, w_weights, S_csr, g0: int = 0, ng: Optio
     return out
 
 
+# --------------------------------------------------------------------------- sparse ingest
+class CsrCounts:
+    """A ``(genes, cells)`` count matrix held on the device as CSR BY CELL (``indptr`` over cells, sorted gene ids,
+    fp32 values) -- the form sparse ``.loom`` / 10x / AnnData HDF5 files store, uploaded as it is (8 bytes per non-zero
+    instead of 8 bytes per ELEMENT of the dense float64 matrix the reference's loader builds, analysis.py:56-64)."""
+
+    __slots__ = ("indptr", "genes", "values", "G")
+
+    def __init__(self, indptr: torch.Tensor, genes: torch.Tensor, values: torch.Tensor, G: int):
+        assert indptr.is_cuda and indptr.dtype == torch.int64 and genes.dtype == torch.int32 and values.dtype == torch.float32
+        self.indptr, self.genes, self.values, self.G = indptr.contiguous(), genes.contiguous(), values.contiguous(), int(G)
+
+    @property
+    def C(self) -> int:
+        return self.indptr.numel() - 1
+
+    @property
+    def nnz(self) -> int:
+        return self.genes.numel()
+
+    @classmethod
+    def from_arrays(cls, indptr, indices, data, G: int) -> "CsrCounts":
+        """From the three arrays of a by-cell compressed layout (HDF5 ``indptr`` / ``indices`` / ``data``)."""
+        device = require_cuda()
+        as_t = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(
+            device=device).to(dt)
+        return cls(as_t(indptr, torch.int64), as_t(indices, torch.int32), as_t(data, torch.float32), G)
+
+    @classmethod
+    def from_scipy(cls, M) -> "CsrCounts":
+        """From a SciPy sparse matrix in the reference's orientation ``(genes, cells)``: its CSC form IS CSR by cell."""
+        from scipy import sparse
+        M = sparse.csc_matrix(M)
+        if not M.has_sorted_indices:
+            M = M.sorted_indices()
+        return cls.from_arrays(M.indptr, M.indices, M.data, M.shape[0])
+
+    def cell_sums(self) -> torch.Tensor:
+        out = torch.empty(self.C, dtype=torch.float64, device=self.values.device)
+        _cabi.call("velo_dev_csr_cell_sums_scale", self.indptr.data_ptr(), self.values.data_ptr(), self.C, 0, out.data_ptr(),
+                   _stream_ptr())
+        return out
+
+    def scaled(self, factor: torch.Tensor) -> "CsrCounts":
+        """``factor[cell] * X`` with the same pattern (size normalisation; non-finite products -> 0)."""
+        assert factor.is_cuda and factor.dtype == torch.float64 and factor.numel() == self.C
+        out = CsrCounts(self.indptr, self.genes, self.values.clone(), self.G)
+        _cabi.call("velo_dev_csr_cell_sums_scale", out.indptr.data_ptr(), out.values.data_ptr(), out.C,
+                   factor.contiguous().data_ptr(), 0, _stream_ptr())
+        return out
+
+    def to_cellmajor(self, g0: int = 0, ng: Optional[int] = None) -> CellMajor:
+        """Dense cell-major gene slab ``[g0, g0 + ng)`` (default: all genes) on the device."""
+        ng = self.G - g0 if ng is None else ng
+        out = CellMajor(torch.empty((self.C, padded_ld(ng)), dtype=torch.float32, device=self.values.device), ng)
+        _cabi.call("velo_dev_csr_to_cellmajor", self.indptr.data_ptr(), self.genes.data_ptr(), self.values.data_ptr(),
+                   self.C, int(g0), int(ng), out.ptr, out.ld, _stream_ptr())
+        return out
+
+
 # --------------------------------------------------------------------------- exact kNN (SURVEY.md 8f item 2)
 KNN_MAX_K = 14000
 # metrics the brute-force kernel serves: Euclidean directly; correlation / cosine through the identity
