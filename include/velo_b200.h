@@ -103,6 +103,14 @@ int velo_transition_prob_partial(int transform, const void *e, const void *d, in
                                  const int64_t *ixs, float *out,
                                  int64_t rows, int64_t cols, int64_t nrndm, double psc, double sigma);
 
+/* Host-side neighbour sampler of estimate_transition_prob with NumPy's legacy random stream, bit for bit
+ * (analysis.py:1529, 1552-1566): equivalent to
+ *     np.random.seed(seed); np.stack([np.random.choice(W, size, replace=False, p=p) for _ in range(n_cells)])
+ * sampling_ixs: n_cells x size int64 (host).  mt_key_out (624 words) / mt_pos_out: the generator state afterwards, so the
+ * caller can leave np.random where the reference would have left it (either may be NULL).  No device work. */
+int velo_host_sample_neighbors_numpy(uint32_t seed, int64_t n_cells, int W, const double *p, int size,
+                                     int64_t *sampling_ixs, uint32_t *mt_key_out, int *mt_pos_out);
+
 /* ---- cell-sharded host tier (one process per GPU) ----
  * The reference parallelises colDeltaCor*partial with an OpenMP prange over cells inside one process
  * (speedboosted.pyx:22-23); at box scale every rank owns a contiguous block of cells [c0, c0 + nc).

@@ -275,9 +275,8 @@ def test_exponential_clock_sampling_is_numpy_choice_without_replacement():
     assert np.abs(p1 - want).max() < tol
 
 
-def test_feistel_cycle_walk_is_a_bijection():
-    """The permutation behind the device randomised control (k_permute_rows_nsign, csrc/random.cu), restated in NumPy:
-    a 4-round Feistel network on 2h bits, cycle-walked into [0, C), is a bijection of the cells for every gene key."""
+def _feistel_numpy(C, g, seed=(0x1234ABCD, 0x9E37)):
+    """k_permute_gene_rows (csrc/random.cu) restated in NumPy: pi_g(c) for all c, and the sign bits."""
     def mix32(x):
         x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
         x ^= x >> 16; x = (x * 0x85EBCA6B) & 0xFFFFFFFF
@@ -285,25 +284,53 @@ def test_feistel_cycle_walk_is_a_bijection():
         x ^= x >> 16
         return x
 
+    h = 1
+    while (1 << (2 * h)) < C:
+        h += 1
+    mask = (1 << h) - 1
+    kg = (mix32(np.uint64(g) ^ np.uint64(seed[0])) + seed[1]) & 0xFFFFFFFF
+    rk = [int(mix32((kg + 0x9E3779B9 * (r + 1)) & 0xFFFFFFFF)) for r in range(4)]
+    x = np.arange(C, dtype=np.uint64)
+    todo = np.ones(C, dtype=bool)
+    first = True
+    while todo.any():
+        L, R = x[todo] >> h, x[todo] & mask
+        for r in range(4):
+            f = ((((R + rk[r]) & 0xFFFFFFFF) * 0x9E3779B1) & 0xFFFFFFFF) >> (32 - h)
+            L, R = R, L ^ f
+        x[todo] = (L << h) | R
+        todo = x >= C if first else todo & (x >= C)
+        first = False
+    sk = int(mix32(kg ^ 0x5bd1e995))
+    c = np.arange(C, dtype=np.uint64)
+    sign = (((((c * 0x9E3779B1) & 0xFFFFFFFF) ^ sk) * 0x85EBCA6B) & 0xFFFFFFFF) >> 31
+    return x.astype(np.int64), sign.astype(np.int64)
+
+
+def test_feistel_cycle_walk_is_a_bijection():
+    """The permutation behind the device randomised control: a 4-round Feistel network on 2h bits, cycle-walked into
+    [0, C), is a bijection of the cells for every gene key -- and, over genes, behaves like independent uniform
+    permutations with fair signs (what permute_rows_nsign, analysis.py:2413-2420, draws from numba's generator)."""
     for C in (1, 2, 3, 72, 1000, 4097):
-        h = 1
-        while (1 << (2 * h)) < C:
-            h += 1
-        mask = (1 << h) - 1
         for g in (0, 1, 12345):
-            kg = (mix32(np.uint64(g) ^ np.uint64(0x1234ABCD)) + 0x9E37) & 0xFFFFFFFF
-            x = np.arange(C, dtype=np.uint64)
-            todo = np.ones(C, dtype=bool)
-            first = True
-            while todo.any():
-                L, R = x[todo] >> h, x[todo] & mask
-                for r in range(4):
-                    f = mix32((R + kg * (2 * r + 1) + 0x9E3779B9 * (r + 1)) & 0xFFFFFFFF) & mask
-                    L, R = R, L ^ f
-                x[todo] = (L << h) | R
-                todo = x >= C if first else todo & (x >= C)
-                first = False
-            assert np.array_equal(np.sort(x), np.arange(C, dtype=np.uint64)), (C, g)
+            x, _ = _feistel_numpy(C, g)
+            assert np.array_equal(np.sort(x), np.arange(C)), (C, g)
+    C, n_genes = 500, 4000
+    perms, signs = zip(*(_feistel_numpy(C, g) for g in range(n_genes)))
+    perms, signs = np.array(perms), np.array(signs)
+    # where cell 0 / cell 137 come from: uniform over the C cells (chi-square, 499 dof: mean 499, sd 31.6)
+    for c in (0, 137):
+        cnt = np.bincount(perms[:, c], minlength=C)
+        chi2 = ((cnt - n_genes / C) ** 2 / (n_genes / C)).sum()
+        assert chi2 < 499 + 5 * 31.6, chi2
+    # neighbouring cells are not mapped to neighbouring sources, fixed points are ~1/C, signs are fair and independent
+    d = np.abs(perms[:, 1:] - perms[:, :-1])
+    assert abs((d == 1).mean() - 2.0 / C) < 1.5e-3
+    assert abs((perms == np.arange(C)[None, :]).mean() - 1.0 / C) < 5e-4
+    assert abs(signs.mean() - 0.5) < 2e-3
+    assert abs(np.corrcoef(signs[:, 3], signs[:, 4])[0, 1]) < 0.06 and abs(np.corrcoef(signs[7], signs[8])[0, 1]) < 0.15
+    # two genes never share a permutation
+    assert len({tuple(p[:16]) for p in perms}) == n_genes
 
 
 def test_normalize_dispatch_matches_reference_interface(monkeypatch):
@@ -387,3 +414,24 @@ def test_sharded_host_front_helpers():
     assert needs_residuals("sqrt", 1.0, 8) and not needs_residuals("sqrt", 1e-10, 8)
     assert not needs_residuals("sqrt", 1.0, 4) and not needs_residuals("linear", 0.0, 8)
     assert needs_residuals("log10", 0.5, 8) and not needs_residuals("log10", 1.0, 8)
+
+
+def test_host_sampler_consumes_numpys_legacy_stream_bit_for_bit():
+    """The C++ restatement of the per-cell ``np.random.choice(..., replace=False, p=p)`` loop (analysis.py:1561-1564):
+    identical samples AND identical generator state afterwards, for the reference's linear probability ramps, a steep
+    ramp with many collisions, and the degenerate size == W case.  No GPU involved."""
+    from velocyto_b200.analysis import _sample_neighbors_numpy_stream
+    for C, W, frac, ramp in ((40, 31, 0.5, (0.5, 0.1)), (60, 2001, 0.3, (0.5, 0.1)), (6, 20001, 0.3, (0.5, 0.1)),
+                             (9, 5, 1.0, (0.5, 0.1)), (25, 501, 0.9, (0.9, 0.001))):
+        p = np.linspace(ramp[0], ramp[1], W)
+        p = p / p.sum()
+        size = int(frac * W)
+        np.random.seed(15071990)
+        want = np.stack([np.random.choice(W, size=(size,), replace=False, p=p) for _ in range(C)], 0)
+        state_want = np.random.get_state()
+        np.random.seed(1)                                              # whatever was there before must not matter
+        got = _sample_neighbors_numpy_stream(15071990, C, W, p, size)
+        state_got = np.random.get_state()
+        assert np.array_equal(got, want), (C, W)
+        assert np.array_equal(state_got[1], state_want[1]) and state_got[2] == state_want[2]
+        assert np.random.random() == (np.random.set_state(state_want) or np.random.random())   # and the NEXT draw agrees

@@ -636,11 +636,22 @@ def test_velocytoloom_medium_pipeline_matches_reference_golden(golden, oracle):
     vlm.normalize("both", size=True, log=True)
     # ---- PCA on the device vs scikit-learn's (exact "full" solver at this size)
     vlm.perform_PCA(n_components=12)
-    scale = np.abs(g["pcs"]).max()
-    np.testing.assert_allclose(vlm.pcs, g["pcs"], rtol=0, atol=2e-6 * scale)
-    np.testing.assert_allclose(vlm.pca.explained_variance_ratio_, g["pca_explained_variance_ratio"], rtol=1e-5)
-    np.testing.assert_allclose(vlm.pca.explained_variance_, g["pca_explained_variance"], rtol=1e-5)
-    np.testing.assert_allclose(vlm.pca.components_[:, :60], g["pca_components_head"], rtol=0, atol=2e-6)
+    # scikit-learn's "auto" policy hands this shape (12 of 260 x 1100) to its RANDOMISED solver with random_state=None:
+    # beyond the well-separated first component the reference's own pcs are approximate and differ from run to run
+    # (tests/golden/make_golden.py stores one such draw).  The device PCA is exact, so it is compared with
+    # scikit-learn's exact solver on the same S_norm, and with the golden draw where that is well defined.
+    from sklearn.decomposition import PCA
+    Sn = vlm.S_norm
+    exact = PCA(n_components=12, svd_solver="full").fit(Sn.T)
+    want = exact.transform(Sn.T)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(vlm.pcs, want, rtol=0, atol=2e-6 * scale)
+    np.testing.assert_allclose(vlm.pca.explained_variance_ratio_, exact.explained_variance_ratio_, rtol=1e-6)
+    np.testing.assert_allclose(vlm.pca.explained_variance_, exact.explained_variance_, rtol=1e-6)
+    np.testing.assert_allclose(vlm.pca.components_, exact.components_, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(vlm.pcs[:, 0], g["pcs"][:, 0], rtol=0, atol=1e-5 * scale)           # the golden draw, PC 1
+    np.testing.assert_allclose(vlm.pca.explained_variance_ratio_[0], g["pca_explained_variance_ratio"][0], rtol=1e-5)
+    assert np.all(vlm.pca.explained_variance_ >= g["pca_explained_variance"] * (1 - 1e-9))         # exact >= randomised estimate
     vlm.pcs = g["pcs"]                       # continue from the reference's components: stage-by-stage identical inputs
     vlm.knn_imputation(k=25, pca_space=True, n_pca_dims=10, balanced=False, n_jobs=1)
     knn_sorted = vlm.knn.copy()
@@ -833,8 +844,9 @@ def test_velocity_threshold_matches_numpy():
     gam, q = rng.uniform(-0.5, 2, G).astype(np.float32), rng.uniform(-1, 1, G).astype(np.float32)
     Sd = dev.CellMajor.from_gene_major(S.astype(np.float64))
     thr = torch.empty(G, dtype=torch.float32, device="cuda")
-    _cabi.call("velo_dev_velocity_threshold", Sd.ptr, Sd.ld, torch.from_numpy(gam).cuda().data_ptr(),
-               torch.from_numpy(q).cuda().data_ptr(), G, C, 0.25, thr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    gam_d, q_d = torch.from_numpy(gam).cuda(), torch.from_numpy(q).cuda()
+    _cabi.call("velo_dev_velocity_threshold", Sd.ptr, Sd.ld, gam_d.data_ptr(), q_d.data_ptr(), G, C, 0.25, thr.data_ptr(),
+               torch.cuda.current_stream().cuda_stream)
     want = 0.25 * (gam[:, None] * S + q[:, None]).max(1)
     np.testing.assert_allclose(thr.cpu().numpy(), want, rtol=2e-6, atol=1e-6)
 

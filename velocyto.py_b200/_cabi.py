@@ -39,6 +39,7 @@ PROTOTYPES = {
     "velo_colDeltaCorLog10partial": (_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _dbl]),
     "velo_colDeltaCorpartial_compact": (_int, [_int, _ptr, _ptr, _int, _ptr, _ptr, _i64, _i64, _i64, _dbl]),
     "velo_transition_prob_partial": (_int, [_int, _ptr, _ptr, _int, _ptr, _ptr, _i64, _i64, _i64, _dbl, _dbl]),
+    "velo_host_sample_neighbors_numpy": (_int, [C.c_uint32, _i64, _int, _ptr, _int, _ptr, _ptr, _ptr]),
     "velo_upload_cellmajor": (_int, [_ptr, _int, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "velo_transition_prob_partial_sharded": (_int, [_int, _ptr, _ptr, _i64, _ptr, _ptr, _int, _i64, _ptr, _ptr,
                                                     _i64, _i64, _i64, _i64, _i64, _dbl, _dbl]),

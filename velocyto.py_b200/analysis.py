@@ -651,8 +651,7 @@ class VelocytoLoom:
                 neigh_ixs = ix_dev.cpu().numpy().astype(np.intp)
             else:
                 neigh_ixs = self.embedding_knn.indices.reshape((-1, n_neighbors + 1))
-                sampling_ixs = np.stack([np.random.choice(neigh_ixs.shape[1], size=(size,), replace=False, p=p)
-                                         for _ in range(neigh_ixs.shape[0])], 0)         # analysis.py:1561-1564
+                sampling_ixs = _sample_neighbors_numpy_stream(random_seed, neigh_ixs.shape[0], neigh_ixs.shape[1], p, size)
                 self.sampling_ixs = sampling_ixs
                 neigh_ixs = neigh_ixs[np.arange(neigh_ixs.shape[0])[:, None], sampling_ixs]
             nonzero = neigh_ixs.shape[0] * neigh_ixs.shape[1]
@@ -786,6 +785,23 @@ for _n in _MATRIX_ATTRS:
     setattr(VelocytoLoom, _n, _DeviceBacked(_n))
 for _n in _DENSE_ATTRS:
     setattr(VelocytoLoom, _n, _LazyDense(_n))
+
+
+def _sample_neighbors_numpy_stream(seed: int, n_cells: int, W: int, p: np.ndarray, size: int) -> np.ndarray:
+    """``np.random.seed(seed); np.stack([np.random.choice(W, size, replace=False, p=p) for _ in range(n_cells)])``
+    (analysis.py:1529, 1561-1564) -- the same MT19937 stream consumed the same way, bit for bit, by the C++ restatement
+    in libvelo_b200 (csrc/host_sampler.cpp) instead of a Python loop of ~1 ms per cell.  NumPy's global generator is
+    left in the state the reference's loop would have left it in."""
+    import ctypes
+    if not 0 <= int(seed) < 2 ** 32:
+        raise ValueError("Seed must be between 0 and 2**32 - 1")
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.empty((n_cells, size), dtype=np.int64)
+    key, pos = np.empty(624, dtype=np.uint32), ctypes.c_int(0)
+    _cabi.call("velo_host_sample_neighbors_numpy", int(seed), n_cells, W, p.ctypes.data, size, out.ctypes.data,
+               key.ctypes.data, ctypes.addressof(pos))
+    np.random.set_state(("MT19937", key, pos.value, 0, 0.0))
+    return out.astype(np.intp, copy=False)
 
 
 # --------------------------------------------------------------------------- host RNG helpers (analysis.py:2407-2420)

@@ -78,13 +78,17 @@ __global__ void __launch_bounds__(1024) k_sample_neighbors(const int32_t *__rest
 
 // out[c, g] = +-in[pi_g(c), g]: pi_g = 4-round Feistel bijection on [0, 4^h) >= C keyed by (seed, g), cycle-walked into
 // [0, C); the sign is an independent hash bit of (seed, g, c).
-__device__ __forceinline__ uint32_t feistel_walk(uint32_t x, uint32_t kg, int h, uint32_t mask, uint32_t C)
+// Round function: the top h bits of an odd-constant product of (R + round key) -- every bit of R reaches them; one
+// add, one multiply, one shift per round (round 1 hashed with a full murmur finaliser per round: ~100 instructions
+// per element made the permutation kernel compute-bound at a tenth of the HBM rate).  Any round function gives a
+// bijection; uniformity / independence of the resulting permutations is tested statistically (tests/test_host_logic.py).
+__device__ __forceinline__ uint32_t feistel_walk(uint32_t x, const uint32_t (&rk)[4], int h, uint32_t mask, uint32_t C)
 {
     do {
         uint32_t L = x >> h, R = x & mask;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint32_t f = mix32(R + kg * (2u * r + 1u) + 0x9E3779B9u * (r + 1u)) & mask;
+            const uint32_t f = ((R + rk[r]) * 0x9E3779B1u) >> (32 - h);
             const uint32_t nl = R;
             R = L ^ f;
             L = nl;
@@ -100,7 +104,7 @@ __device__ __forceinline__ uint32_t feistel_walk(uint32_t x, uint32_t kg, int h,
 // is permuted by ONE CTA that stages the whole row in shared memory with TMA bulk copies (200 KB at 50k cells; rows
 // beyond the shared-memory limit gather from the L2-resident row), and the block is transposed back.  Three
 // streaming passes (6 x the matrix in traffic) instead of one pass that wastes 7/8 of every sector.
-__global__ void __launch_bounds__(512) k_permute_gene_rows(const float *__restrict__ in_gm, float *__restrict__ out_gm,
+__global__ void __launch_bounds__(1024) k_permute_gene_rows(const float *__restrict__ in_gm, float *__restrict__ out_gm,
                                                            int64_t C, int64_t g_first, uint64_t seed, int h, int in_smem)
 {
     extern __shared__ __align__(128) unsigned char perm_smem[];
@@ -136,10 +140,13 @@ __global__ void __launch_bounds__(512) k_permute_gene_rows(const float *__restri
     const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
     const uint32_t kg = mix32(static_cast<uint32_t>(g) ^ s0) + s1;
     const uint32_t sk = mix32(kg ^ 0x5bd1e995u);
+    uint32_t rk[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rk[r] = mix32(kg + 0x9E3779B9u * (r + 1u));          // per-gene round keys, hoisted
     float *orow = out_gm + gl * C;
     for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
-        const uint32_t x = feistel_walk(static_cast<uint32_t>(c), kg, h, mask, static_cast<uint32_t>(C));
-        const uint32_t sbit = mix32(static_cast<uint32_t>(c) * 0x9E3779B1u ^ sk) & 1u;
+        const uint32_t x = feistel_walk(static_cast<uint32_t>(c), rk, h, mask, static_cast<uint32_t>(C));
+        const uint32_t sbit = ((static_cast<uint32_t>(c) * 0x9E3779B1u ^ sk) * 0x85EBCA6Bu) >> 31;
         const float v = row[x];
         orow[c] = sbit ? -v : v;
     }
@@ -202,7 +209,7 @@ extern "C" int velo_dev_permute_rows_nsign(const float *in_cm, float *out_cm, in
     for (int64_t g0 = 0; g0 < G && e == cudaSuccess && rc == VELO_OK; g0 += gb) {
         const int64_t ng = G - g0 < gb ? G - g0 : gb;
         if ((rc = velo_dev_unpack_genemajor(in_cm + g0, ld, ng, C, a, 4, stream))) break;
-        k_permute_gene_rows<<<static_cast<unsigned>(ng), 512, smem, st>>>(a, b, C, g0, seed, h, in_smem);
+        k_permute_gene_rows<<<static_cast<unsigned>(ng), 1024, smem, st>>>(a, b, C, g0, seed, h, in_smem);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
