@@ -144,6 +144,17 @@ def connectivity_with_diagonal(knn, diag: float = 1) -> sparse.csr_matrix:
     milliseconds.  Zero-distance edges are dropped exactly as ``knn > 0`` drops them."""
     knn = sparse.csr_matrix(knn)
     n = knn.shape[0]
+    k = knn.indptr[1] - knn.indptr[0] if n else 0
+    if n and knn.indptr[-1] == n * k and np.array_equal(knn.indptr, np.arange(0, n * k + 1, k)):
+        # regular graph (k entries per row: what the kNN searches return) -- work on (n, k) blocks, no per-edge row ids
+        idx2, dat2 = knn.indices.reshape(n, k), knn.data.reshape(n, k)
+        if (dat2 > 0).all() and (idx2 != np.arange(n, dtype=idx2.dtype)[:, None]).all():
+            indices = np.empty((n, k + 1), dtype=np.int32)
+            indices[:, 0] = np.arange(n, dtype=np.int32)          # diagonal first in every row
+            indices[:, 1:] = idx2
+            data = np.ones((n, k + 1), dtype=np.float64)
+            data[:, 0] = diag
+            return sparse.csr_matrix((data.ravel(), indices.ravel(), np.arange(0, n * (k + 1) + 1, k + 1)), shape=knn.shape)
     rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(knn.indptr))
     keep = (knn.data > 0) & (knn.indices != rows)                 # the diagonal is overwritten by setdiag anyway
     counts = np.bincount(rows[keep], minlength=n) + 1             # + the diagonal entry
@@ -566,8 +577,9 @@ class VelocytoLoom:
         for stale in ("corrcoef_random", "transition_prob_random"):
             if stale in self.__dict__.get("_dense", {}) or stale in self.__dict__.get("_dense_src", {}):
                 delattr(self, stale)
-        _numba_seed(random_seed)                                                         # analysis.py:1501
-        self.which_hidim = hidim
+        if calculate_randomized and random_backend == "reference":
+            _numba_seed(random_seed)                                                     # analysis.py:1501 (only the randomised
+        self.which_hidim = hidim                                                         # control consumes numba's stream, :2413-2420)
         if "n_neighbors" in kwargs:
             n_neighbors = kwargs.pop("n_neighbors")
             if len(kwargs) > 0:
@@ -823,11 +835,11 @@ def _jit_helpers():
     if _JIT is None:
         from numba import jit
 
-        @jit(nopython=True)
+        @jit(nopython=True, cache=True)
         def seed(value):
             np.random.seed(value)
 
-        @jit(nopython=True)
+        @jit(nopython=True, cache=True)
         def permute(A):
             plmi = np.array([+1, -1])
             for i in range(A.shape[0]):

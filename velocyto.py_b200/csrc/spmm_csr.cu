@@ -44,16 +44,38 @@ __global__ void __launch_bounds__(256) k_knn_smooth_csr(const int64_t *__restric
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t p0 = w_indptr[c], p1 = w_indptr[c + 1];
-    for (int64_t p = p0 + warp; p < p1; p += nwarps) {
-        const int64_t j = w_indices[p];
-        const double w = static_cast<double>(w_weights[p]) * kFixScale;
+    // Every warp walks the CSR rows of its share of the neighbours.  The walk is a chain of dependent loads
+    // (neighbour id -> row bounds -> entries), so a warp keeps TWO neighbours in flight, and the two binary searches
+    // for the tile's sub-range are skipped when the row's first and last gene already lie inside the tile (always,
+    // when a rank holds just its own gene slab -- the gene-sharded configuration): round 2 measured the searched
+    // version at 0.33 of the HBM rate by SURVEY 8(d)'s byte count, latency-bound.
+    auto bounds = [&](int64_t j, int64_t &a, int64_t &b) {
         const int64_t r0 = s_indptr[j], r1 = s_indptr[j + 1];
-        const int64_t a = lower_bound_i32(s_genes, r0, r1, gene_lo);           // uniform across the warp
-        const int64_t b = lower_bound_i32(s_genes, a, r1, gene_hi);
+        a = r0;
+        b = r1;
+        if (r1 > r0) {
+            const int32_t first = s_genes[r0], last = s_genes[r1 - 1];
+            if (first < gene_lo) a = lower_bound_i32(s_genes, r0, r1, gene_lo);           // uniform across the warp
+            if (last >= gene_hi) b = lower_bound_i32(s_genes, a, r1, gene_hi);
+        }
+    };
+    auto scatter = [&](int64_t a, int64_t b, double w) {
         for (int64_t q = a + lane; q < b; q += 32) {
             const long long v = __double2ll_rn(w * static_cast<double>(s_values[q]));
             atomicAdd(reinterpret_cast<unsigned long long *>(&acc[s_genes[q] - gene_lo]), static_cast<unsigned long long>(v));
         }
+    };
+    for (int64_t p = p0 + warp; p < p1; p += 2 * nwarps) {
+        const int64_t pB = p + nwarps;
+        const bool hasB = pB < p1;
+        const int64_t jA = w_indices[p], jB = hasB ? w_indices[pB] : jA;
+        const double wA = static_cast<double>(w_weights[p]) * kFixScale;
+        const double wB = hasB ? static_cast<double>(w_weights[pB]) * kFixScale : 0.0;
+        int64_t aA, bA, aB, bB;
+        bounds(jA, aA, bA);
+        bounds(jB, aB, bB);
+        scatter(aA, bA, wA);
+        if (hasB) scatter(aB, bB, wB);
     }
     __syncthreads();
     float *orow = out + c * ld_out + t0;

@@ -563,15 +563,27 @@ class PCAResult:
         return (np.asarray(X) - self.mean_) @ self.components_.T
 
 
-def pca(X: CellMajor, n_components: Optional[int] = None, div_by_std: bool = False, block: int = 8192):
-    """Exact PCA of the cells (rows = samples, genes = features) as ``PCA(n_components).fit_transform(X.T)`` computes it
+PCA_EXACT_MAX_DIM = 4096        # symmetric eigendecomposition up to this order (~1 s); beyond it, subspace iteration
+
+
+def pca(X: CellMajor, n_components: Optional[int] = None, div_by_std: bool = False, block: int = 8192,
+        n_iter: int = 12, seed: int = 0):
+    """PCA of the cells (rows = samples, genes = features) as ``PCA(n_components).fit_transform(X.T)`` defines it
     (analysis.py:697-702): features centred, components = leading right singular vectors with scikit-learn's sign rule
     (largest-magnitude loading positive), ``pcs = U * S``.
 
-    The matrix stays on the device: fp64 second moments accumulated over cell blocks -- the gene x gene covariance,
-    or the cell x cell Gram matrix when there are fewer cells than genes -- one symmetric eigendecomposition
-    (cuSOLVER through ``torch.linalg.eigh``: a plain library call, PCA is not part of the hand-written hot path), and
-    a projection GEMM.  Returns ``(pcs (C, n) float64 CUDA, PCAResult)``."""
+    The matrix stays on the device (fp32 storage, fp64 arithmetic over cell blocks).  Two solvers:
+
+    * exact -- fp64 second moments (gene x gene covariance, or the cell x cell Gram matrix when there are fewer cells
+      than genes) and one symmetric eigendecomposition -- whenever the smaller dimension is at most
+      ``PCA_EXACT_MAX_DIM`` or most components are wanted;
+    * block subspace iteration with Rayleigh-Ritz extraction otherwise (``n_iter`` applications of X_c^T X_c to a
+      random ``n + max(16, n)``-column block, QR after each): the deterministic-seed counterpart of the randomised
+      solver scikit-learn's ``svd_solver="auto"`` picks for such shapes (7 power iterations, 10 oversamples, and a
+      different random block on every call) -- same class of approximation, run much further.
+
+    cuSOLVER / cuBLAS through torch.linalg: plain library calls, PCA is not part of the hand-written hot path.
+    Returns ``(pcs (C, n) float64 CUDA, PCAResult)``."""
     C, G, dv = X.C, X.G, X.t.device
     n = min(C, G) if n_components is None else int(n_components)
     if not 0 < n <= min(C, G):
@@ -587,7 +599,8 @@ def pca(X: CellMajor, n_components: Optional[int] = None, div_by_std: bool = Fal
     for r0 in range(0, C, block):
         mean += rows(r0).sum(0)
     mean /= C
-    if G <= C:                                      # covariance route: G x G
+    exact = min(C, G) <= PCA_EXACT_MAX_DIM or n > min(C, G) // 4
+    if exact and G <= C:                            # covariance route: G x G
         M = torch.zeros((G, G), dtype=torch.float64, device=dv)
         for r0 in range(0, C, block):
             Xb = rows(r0) - mean
@@ -595,13 +608,36 @@ def pca(X: CellMajor, n_components: Optional[int] = None, div_by_std: bool = Fal
         lam, V = torch.linalg.eigh(M)
         lam, V = lam.flip(0)[:n].clamp_min(0), V.flip(1)[:, :n]                # descending
         comps = V.t().contiguous()                                              # (n, G)
-    else:                                           # Gram route: C x C, components = X_c^T u / s
+        del M
+    elif exact:                                     # Gram route: C x C, components = X_c^T u / s
         Xc = torch.cat([rows(r0) - mean for r0 in range(0, C, block)])
         lam, Uv = torch.linalg.eigh(Xc @ Xc.t())
         lam, Uv = lam.flip(0)[:n].clamp_min(0), Uv.flip(1)[:, :n]
         comps = (Xc.t() @ Uv / lam.sqrt().clamp_min(1e-300)).t().contiguous()
         comps = comps / torch.linalg.vector_norm(comps, dim=1, keepdim=True).clamp_min(1e-300)
         del Xc
+    else:                                           # block subspace iteration on X_c^T X_c (G x G, never formed)
+        ell = min(min(C, G), n + max(16, n))
+        gen = torch.Generator(device=dv).manual_seed(seed)
+        Q = torch.linalg.qr(torch.randn((G, ell), dtype=torch.float64, device=dv, generator=gen)).Q
+
+        def apply(Q):                               # returns X_c^T (X_c Q)  and  (X_c Q)^T (X_c Q)
+            Z = torch.zeros((G, ell), dtype=torch.float64, device=dv)
+            T = torch.zeros((ell, ell), dtype=torch.float64, device=dv)
+            for r0 in range(0, C, block):
+                Xb = rows(r0) - mean
+                Y = Xb @ Q
+                Z.addmm_(Xb.t(), Y)
+                T.addmm_(Y.t(), Y)
+            return Z, T
+
+        for _ in range(n_iter):
+            Z, _ = apply(Q)
+            Q = torch.linalg.qr(Z).Q
+        _, T = apply(Q)                             # Rayleigh-Ritz on the converged block
+        lam, Wv = torch.linalg.eigh(T)
+        lam, Wv = lam.flip(0)[:n].clamp_min(0), Wv.flip(1)[:, :n]
+        comps = (Q @ Wv).t().contiguous()
     # scikit-learn's svd_flip(u_based_decision=False): the largest-magnitude loading of every component is positive
     piv = comps.abs().argmax(dim=1)
     sign = torch.sign(comps[torch.arange(n, device=dv), piv])
@@ -616,6 +652,7 @@ def pca(X: CellMajor, n_components: Optional[int] = None, div_by_std: bool = Fal
     ev = lam / (C - 1)
     res = PCAResult(comps.cpu().numpy(), ev.cpu().numpy(), (ev / (total_var / (C - 1))).cpu().numpy(),
                     lam.sqrt().cpu().numpy(), mean.cpu().numpy(), C)
+    res.solver = "exact" if exact else f"subspace_iteration(n_iter={n_iter}, block={ell})"
     return pcs, res
 
 
