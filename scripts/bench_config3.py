@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--cells", type=int, default=50_000)
     ap.add_argument("--genes", type=int, default=30_000)
     ap.add_argument("--skip-sqrt", action="store_true")
+    ap.add_argument("--skip-fp32", action="store_true", help="skip the fp32 K2 kernels (11 s + 19 s at full size)")
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     C, G = a.cells, a.genes
@@ -61,23 +62,37 @@ def main():
         torch.cuda.synchronize()
         return t0.elapsed_time(t1) / reps, sampler.stop(), (_cabi.launch_count() - l0) // reps
 
-    ms, clocks, launches = timed(lambda: dev.coldeltacor_linear_tc(e, d, stats=stats, out=out), a.reps)
-    tf = 12.0 * pg / (ms * 1e-3) / 1e12
-    peak = peaks["bf16_tflops_sustained"] if ms > 200 else peaks["bf16_tflops"]
-    print(json.dumps({
-        "kernel": "K2g k_coldeltacor_tc2 (all-pairs linear, tcgen05 cta_group::2) + operand prep",
-        "workload": f"{C} cells x {G} genes, full C x C (BASELINE config 3)", "ms": ms, "cells_per_s": C / (ms * 1e-3),
-        "pair_gene_per_s": pg / (ms * 1e-3), "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-                     "flop_model": "12 flop per pair-gene: P = B X^T and Q = X X^T, each hi*hi + hi*lo + lo*hi in fp16",
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops%s (cuBLAS)" % ("_sustained" if ms > 200 else ""),
-                     "burst_peak": peaks["bf16_tflops"], "sustained_peak": peaks["bf16_tflops_sustained"]},
-        "clocks": clocks}))
+    nI, nJ = (C + 127) // 128, (C + 255) // 256
+    tiles_all = nI * nJ
+    tiles_upper = sum(1 for ti in range(nI) for tj in range(nJ) if tj >= ti // 2)
+    tiles_lower = sum(1 for u in range((nI + 1) // 2) for tj in range(nJ) if tj < u)
+    for sym in ("0", "1"):
+        os.environ["VELO_TC_SYMMETRIC"] = sym
+        ms, clocks, launches = timed(lambda: dev.coldeltacor_linear_tc(e, d, stats=stats, out=out), a.reps)
+        tf = 12.0 * pg / (ms * 1e-3) / 1e12
+        executed = 1.0 if sym == "0" else (tiles_upper + tiles_lower) / tiles_all       # MMA tile passes actually issued
+        peak = peaks["bf16_tflops_sustained"] if ms > 200 else peaks["bf16_tflops"]
+        print(json.dumps({
+            "kernel": "K2g k_coldeltacor_tc2 (all-pairs linear, tcgen05 cta_group::2) + operand prep"
+                      + (" -- symmetric-Q scheme (two launches)" if sym == "1" else " -- plain scheme (VELO_TC_SYMMETRIC=0)"),
+            "workload": f"{C} cells x {G} genes, full C x C (BASELINE config 3)", "ms": ms, "cells_per_s": C / (ms * 1e-3),
+            "pair_gene_per_s": pg / (ms * 1e-3), "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                         "flop_model": "USEFUL flops: 12 per pair-gene (P = B X^T and Q = X X^T, each hi*hi + hi*lo + lo*hi in fp16), "
+                                       "whatever the scheme executes",
+                         "executed_fraction_of_model": executed, "executed_tflops": tf * executed,
+                         "executed_frac_of_peak": tf * executed / peak,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops%s (cuBLAS)" % ("_sustained" if ms > 200 else ""),
+                         "burst_peak": peaks["bf16_tflops"], "sustained_peak": peaks["bf16_tflops_sustained"]},
+            "clocks": clocks}))
+    os.environ.pop("VELO_TC_SYMMETRIC", None)
     tp = torch.empty_like(out)
     ms_tp, _, _ = timed(lambda: dev.transition_prob(out, None, 0.05, out=tp), 2)
     print(json.dumps({"kernel": "k_transition_prob (full mode epilogue)", "ms": ms_tp,
                       "achieved_gbs": 2 * C * C * 4 / (ms_tp * 1e-3) / 1e9}))
     del tp
+    if a.skip_fp32:
+        return
     lib = _cabi.load()
     lib.velo_set_tensor_cores(0)
     try:

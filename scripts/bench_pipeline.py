@@ -38,14 +38,27 @@ timed("normalize('both') again (resident)", lambda: vlm.normalize("both", size=T
 timed("perform_PCA(n_components=25)", lambda: vlm.perform_PCA(n_components=25))
 timed(f"knn_imputation(k={k}, n_pca_dims=20) [device kNN + K5 x2]", lambda: vlm.knn_imputation(k=k, n_pca_dims=20, n_jobs=8))
 timed("knn_imputation again", lambda: vlm.knn_imputation(k=k, n_pca_dims=20, n_jobs=8))
-timed("fit_gammas() default (weights + box-constrained fit)", lambda: vlm.fit_gammas())
+timed("fit_gammas() default (weights + box-constrained fit) [first call]", lambda: vlm.fit_gammas())
+timed("fit_gammas() default again", lambda: vlm.fit_gammas())
 timed("fit_gammas(weighted=False, fit_offset=False)", lambda: vlm.fit_gammas(weighted=False, fit_offset=False))
 vlm.fit_gammas(weighted=False, fit_offset=True)
 timed("predict_U + calculate_velocity + calculate_shift + extrapolate_cell_at_t",
       lambda: (vlm.predict_U(), vlm.calculate_velocity(), vlm.calculate_shift(), vlm.extrapolate_cell_at_t(delta_t=1.0)))
 vlm.ts = vlm.pcs[:, :2].copy()
 kw = dict(hidim="Sx_sz", embed="ts", transform="sqrt", psc=1, n_neighbors=NN, knn_random=True, sampled_fraction=0.3, n_jobs=8)
-timed(f"estimate_transition_prob(n_neighbors={NN}, frac 0.3, randomized) random_backend='device'",
+timed(f"estimate_transition_prob(n_neighbors={NN}, frac 0.3, randomized) random_backend='device' [first call]",
+      lambda: vlm.estimate_transition_prob(random_backend="device", **kw))
+if os.environ.get("PROFILE", "0") == "1":
+    import cProfile, pstats, io
+    pr = cProfile.Profile()
+    pr.enable()
+    vlm.estimate_transition_prob(random_backend="device", **kw)
+    torch.cuda.synchronize()
+    pr.disable()
+    buf = io.StringIO()
+    pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(18)
+    print(buf.getvalue(), file=sys.stderr)
+timed(f"estimate_transition_prob(n_neighbors={NN}, frac 0.3, randomized) random_backend='device' again",
       lambda: vlm.estimate_transition_prob(random_backend="device", **kw))
 timed("calculate_embedding_shift(expression_scaling=True) [after device backend]",
       lambda: vlm.calculate_embedding_shift(sigma_corr=0.05, expression_scaling=True))

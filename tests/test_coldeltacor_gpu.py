@@ -593,3 +593,25 @@ def test_transition_prob_small_sigma_and_nan_rules():
         np.testing.assert_allclose(got, want, rtol=5e-5 if sigma < 0.01 else 2e-6, atol=1e-30)
     got = dev.transition_prob(torch.from_numpy(corr).cuda(), dev.indices_to_device(ix, 300), 0.05, patch_nan=False).cpu().numpy()
     assert np.isnan(got[5]).all() and np.isfinite(np.delete(got, 5, 0)).all()
+
+
+@pytest.mark.parametrize("C", [1300, 1537])
+def test_tensor_core_symmetric_scheme_matches_plain(oracle, C, monkeypatch):
+    """K2g symmetric-Q scheme (launch 1: tiles on/right of the diagonal compute P and Q and keep Q; launch 2: tiles left
+    of it compute two P tiles and read Q[c, i] = Q[i, c]) against the plain scheme and the oracle -- odd and even
+    numbers of 128-cell blocks, a ragged last block."""
+    from velocyto_b200 import device as dev
+    G = 900
+    e, d = _tc_inputs(G, C, 77)
+    e_cm, d_cm = dev.CellMajor.from_gene_major(e), dev.CellMajor.from_gene_major(d)
+    monkeypatch.setenv("VELO_TC_SYMMETRIC", "0")
+    plain = dev.coldeltacor_linear_tc(e_cm, d_cm).cpu().numpy()
+    monkeypatch.setenv("VELO_TC_SYMMETRIC", "1")
+    sym, P, Q = dev.coldeltacor_linear_tc(e_cm, d_cm, debug=True)
+    sym, Q = sym.cpu().numpy(), Q.cpu().numpy()
+    off = ~np.eye(C, dtype=bool)
+    assert np.array_equal(np.isnan(sym), np.isnan(plain))
+    np.testing.assert_allclose(sym[off], plain[off], rtol=0, atol=2e-7)
+    np.testing.assert_allclose(Q, Q.T, rtol=1e-6, atol=1e-6 * np.abs(Q).max())          # what the scheme relies on
+    want = oracle.coldeltacor(e, d, None, "linear", 0.0)
+    np.testing.assert_allclose(sym[off], want[off], rtol=0, atol=5e-7)

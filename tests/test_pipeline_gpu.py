@@ -617,7 +617,7 @@ def _oracle_chain_medium(vo, g):
     U_sz = vo.size_log_normalize(U, guard=True)[0]
     C = S.shape[1]
     knn = sparse.csr_matrix((g["knn_data"], g["knn_indices"], g["knn_indptr"]), shape=(C, C))
-    Sx, Ux = vo.knn_imputation(S_sz, U_sz, knn)
+    Sx, Ux, _ = vo.knn_imputation(S_sz, U_sz, knn)
     gam, q = vo.fit_slope_offset(np.ascontiguousarray(Ux), np.ascontiguousarray(Sx))
     Upred = vo.predict_U(gam, Sx, q)
     dS = vo.calculate_shift(vo.calculate_velocity(Ux, Upred), 1.0)

@@ -25,6 +25,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "velo_common.cuh"
 
 namespace velo {
@@ -62,6 +64,11 @@ struct TcParams {
     int nkb;                // pipeline stages over the gene axis (Gp / kBK)
     int drain_groups;       // 64-gene groups per TMEM drain (1 in production; > 1 only to measure the accumulation bias)
     int nI, nJ;             // tile counts (cells, targets)
+    // symmetric-Q scheme of the pair kernel (whole problem on one GPU: c0 == 0, nc == C); see k_coldeltacor_tc2
+    const int2 *tiles;      // explicit (ti, tj) list for modes 1 / 2, nullptr = rasterise all nI x nJ tiles (mode 0)
+    float *qscratch;        // C x C fp32: Q[c, i] written by mode 1, read transposed by mode 2
+    int mode;               // 0: P and Q for every tile; 1: tiles on/right of the diagonal, also stores Q;
+                            // 2: tiles left of the diagonal, TWO P tiles per pair (no Q MMAs), Q[c,i] = Q[i,c] from scratch
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -430,7 +437,11 @@ k_coldeltacor_tc2(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
     const uint32_t rank = cluster_ctarank();
 
     int ti, tj;   // pair tile: 128 cells x 256 targets; groups of kRasterGroup cell blocks, targets fastest inside a group
-    {
+    if (p.tiles) {
+        const int2 t = p.tiles[blockIdx.x >> 1];     // modes 1 / 2: host-built list (same raster idea, triangular sets)
+        ti = t.x;                                    // mode 2: index u of the PAIR of cell blocks (2u, 2u + 1)
+        tj = t.y;
+    } else {
         const int64_t t = blockIdx.x >> 1;
         const int64_t per_group = static_cast<int64_t>(kRasterGroup) * p.nJ;
         const int g = static_cast<int>(t / per_group);
@@ -466,8 +477,13 @@ k_coldeltacor_tc2(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
         if (lane == 0) {
-            const CUtensorMap *tmAh = rank ? &tmXh : &tmBh, *tmAl = rank ? &tmXl : &tmBl;
-            const int32_t rowA = rank ? static_cast<int32_t>(p.c0) + ti * kTM : ti * kTM;
+            // modes 0 / 1: A rows 0..127 (CTA 0) = the cells' b rows, 128..255 (CTA 1) = the same cells' x rows.
+            // mode 2: BOTH halves are b rows -- of cell block 2u in CTA 0 and 2u + 1 in CTA 1 -- so the one M = 256
+            // instruction stream yields two P tiles and no Q (it comes from the scratch, by symmetry).
+            const bool two_p = p.mode == 2;
+            const CUtensorMap *tmAh = (rank && !two_p) ? &tmXh : &tmBh, *tmAl = (rank && !two_p) ? &tmXl : &tmBl;
+            const int32_t rowA = two_p ? (2 * ti + static_cast<int32_t>(rank)) * kTM
+                                       : (rank ? static_cast<int32_t>(p.c0) + ti * kTM : ti * kTM);
             const int32_t rowJ = tj * kTN + static_cast<int32_t>(rank) * 128;
             for (int kb = 0; kb < p.nkb; ++kb) {
                 const int s = kb % kStages;
@@ -545,7 +561,39 @@ k_coldeltacor_tc2(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
         for (int j = 0; j < 128; ++j) sS[row * kEpiPitch + h * 128 + j] = acc[j];
     }
     cluster_sync();                              // both tiles parked and visible cluster-wide
-    if (warp >= 2) {
+    if (warp >= 2 && p.mode == 2) {
+        // two P tiles: CTA r owns all 128 rows of cell block 2u + r; P from its OWN parked sums, Q[c, i] = Q[i, c] from
+        // the scratch mode 1 filled (row i of the scratch, column c: a strided read, 4 bytes per 32-byte sector --
+        // C^2 / 2 such reads are ~15 ms at 50k cells against the ~0.2 s of MMAs they replace)
+        const float *sS = reinterpret_cast<const float *>(aligned);
+        const int ew = warp - 2;
+        for (int row = ew; row < 128; row += kEpiWarps) {
+            const int64_t r = (2 * static_cast<int64_t>(ti) + rank) * kTM + row;
+            if (r >= p.nc) break;
+            const int64_t c = r;                                   // c0 == 0 in this mode
+            const double qc = p.qd[c], pc = p.pcc[r], sb = p.stats[2 * r + 1];
+            const double isb_r = p.isb[r];
+#pragma unroll
+            for (int cc = 0; cc < kTN / 32; ++cc) {
+                const int col = cc * 32 + lane;
+                const int64_t i = static_cast<int64_t>(tj) * kTN + col;
+                if (i < p.C) {
+                    const double qi = p.qd[i], isx_i = p.isx[i];
+                    const double Pt = static_cast<double>(sS[row * kEpiPitch + col]) * (isb_r * isx_i);
+                    const double Qt = static_cast<double>(__ldg(p.qscratch + i * p.C + c));
+                    const double dist2 = qc + qi - 2.0 * Qt;
+                    const double num = Pt - pc;
+                    const bool degenerate = (i == c) || !(dist2 > 4e-6 * (qc + qi)) || !(sb > 0.0);
+                    p.out[r * p.out_ld + i] =
+                        degenerate ? __int_as_float(0x7fc00000) : static_cast<float>(num * rsqrt(dist2 * sb));
+                    if (p.dbgP) {
+                        p.dbgP[r * p.out_ld + i] = static_cast<float>(Pt);
+                        p.dbgQ[r * p.out_ld + i] = static_cast<float>(Qt);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 2) {
         // CTA r finishes rows 64*r .. 64*r+63 of the pair tile: P from CTA 0's shared memory, Q from CTA 1's
         const uint32_t sbase = smem_u32(aligned);
         const uint32_t baseP = mapa(sbase, 0), baseQ = mapa(sbase, 1);
@@ -571,6 +619,8 @@ k_coldeltacor_tc2(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                     const bool degenerate = (i == c) || !(dist2 > 4e-6 * (qc + qi)) || !(sb > 0.0);
                     p.out[r * p.out_ld + i] =
                         degenerate ? __int_as_float(0x7fc00000) : static_cast<float>(num * rsqrt(dist2 * sb));
+                    // mode 1: keep Q for the mirrored pair (the scales are powers of two: the fp32 store is exact)
+                    if (p.mode == 1) p.qscratch[c * p.C + i] = static_cast<float>(Qt);
                     if (p.dbgP) {
                         p.dbgP[r * p.out_ld + i] = static_cast<float>(Pt);
                         p.dbgQ[r * p.out_ld + i] = static_cast<float>(Qt);
@@ -792,7 +842,9 @@ extern "C" int velo_get_tensor_cores(void) { return g_tensor_cores.load(); }
 extern "C" size_t velo_coldeltacor_tc_workspace_bytes(int64_t G, int64_t C, int64_t nc)
 {
     const int64_t Gp = round_up(G, tc::kGroup);
-    return static_cast<size_t>(2 * (C + nc) * Gp * 2 + (C + nc) * 12 + G * 4 + 64 * G * 8 + 4096);
+    // + the C x C fp32 copy of Q that the symmetric scheme keeps when the whole problem is on one GPU (nc == C)
+    return static_cast<size_t>(2 * (C + nc) * Gp * 2 + (C + nc) * 12 + G * 4 + 64 * G * 8 + 4096) +
+           (nc == C ? static_cast<size_t>(C) * C * 4 : 0);
 }
 
 extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int64_t ld, const float *stats, float *out,
@@ -871,6 +923,7 @@ extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int
         if (v >= 1 && v <= 4096) p.drain_groups = v;
     }
     p.nI = static_cast<int>((nc + kTM - 1) / kTM);
+    p.tiles = nullptr; p.qscratch = nullptr; p.mode = 0;
     // variant: 2 = CTA pairs (cta_group::2, 128 x 256 pair tiles; default), 1 = single CTAs (128 x 128 tiles)
     int variant = 2;
     if (const char *env = getenv("VELO_TC_VARIANT")) variant = atoi(env) == 1 ? 1 : 2;
@@ -892,8 +945,56 @@ extern "C" int velo_dev_coldeltacor_tc(const float *e_cm, const float *d_cm, int
                      "coldeltacor_tc: needs %zu bytes of shared memory", tc2::kSmemBytes);
         VELO_CUDA_TRY(cudaFuncSetAttribute(tc2::k_coldeltacor_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(tc2::kSmemBytes)));
-        tc2::k_coldeltacor_tc2<<<static_cast<unsigned>(2 * pairs), kThreads, tc2::kSmemBytes, st>>>(tmXh, tmXl, tmBh,
-                                                                                                   tmBl, p);
+        // Symmetric-Q scheme: Q = X X^T is symmetric, so when the WHOLE problem is on this GPU only the tiles on or
+        // right of the diagonal compute it (launch 1, which also stores it: C x C fp32 scratch); the tiles left of the
+        // diagonal (launch 2) spend both halves of the M = 256 instruction on P tiles of two adjacent cell blocks and
+        // read Q[c, i] = Q[i, c] back: 0.5 + 0.25 = 0.75 of the MMA cycles.  VELO_TC_SYMMETRIC=0 switches it off.
+        bool symmetric = c0 == 0 && nc == C && p.nI >= 4;
+        if (const char *env = getenv("VELO_TC_SYMMETRIC")) symmetric = symmetric && atoi(env) != 0;
+        size_t free_b = 0, total_b = 0;
+        if (symmetric && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            symmetric = static_cast<size_t>(C) * C * 4 + (2ull << 30) < free_b;
+        Scratch qs, tl1, tl2;
+        if (symmetric && qs.alloc(static_cast<size_t>(C) * C * 4, st) != VELO_OK) {
+            (void)cudaGetLastError();
+            symmetric = false;
+        }
+        if (!symmetric) {
+            p.tiles = nullptr; p.qscratch = nullptr; p.mode = 0;
+            tc2::k_coldeltacor_tc2<<<static_cast<unsigned>(2 * pairs), kThreads, tc2::kSmemBytes, st>>>(tmXh, tmXl, tmBh,
+                                                                                                       tmBl, p);
+        } else {
+            std::vector<int2> upper, lower;
+            for (int g0 = 0; g0 < p.nI; g0 += kRasterGroup) {          // launch 1: tj >= ti / 2, groups of cell blocks
+                const int g1 = g0 + kRasterGroup < p.nI ? g0 + kRasterGroup : p.nI;
+                for (int tj = g0 >> 1; tj < p.nJ; ++tj)
+                    for (int ti = g0; ti < g1; ++ti)
+                        if (tj >= (ti >> 1)) upper.push_back(make_int2(ti, tj));
+            }
+            const int nU = (p.nI + 1) / 2;                             // launch 2: pairs u of cell blocks, tj < u
+            for (int g0 = 0; g0 < nU; g0 += kRasterGroup / 2) {
+                const int g1 = g0 + kRasterGroup / 2 < nU ? g0 + kRasterGroup / 2 : nU;
+                for (int tj = 0; tj < g1 - 1 && tj < p.nJ; ++tj)
+                    for (int u = g0; u < g1; ++u)
+                        if (tj < u) lower.push_back(make_int2(u, tj));
+            }
+            if ((rc = tl1.alloc(upper.size() * sizeof(int2), st))) return rc;
+            if ((rc = tl2.alloc(lower.size() * sizeof(int2) + 16, st))) return rc;
+            VELO_CUDA_TRY(cudaMemcpyAsync(tl1.p, upper.data(), upper.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+            if (!lower.empty())
+                VELO_CUDA_TRY(cudaMemcpyAsync(tl2.p, lower.data(), lower.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+            VELO_CUDA_TRY(cudaStreamSynchronize(st));                  // the host vectors go out of scope below
+            p.qscratch = static_cast<float *>(qs.p);
+            p.tiles = static_cast<const int2 *>(tl1.p); p.mode = 1;
+            tc2::k_coldeltacor_tc2<<<static_cast<unsigned>(2 * upper.size()), kThreads, tc2::kSmemBytes, st>>>(
+                tmXh, tmXl, tmBh, tmBl, p);
+            VELO_LAUNCH_CHECK();
+            if (!lower.empty()) {
+                p.tiles = static_cast<const int2 *>(tl2.p); p.mode = 2;
+                tc2::k_coldeltacor_tc2<<<static_cast<unsigned>(2 * lower.size()), kThreads, tc2::kSmemBytes, st>>>(
+                    tmXh, tmXl, tmBh, tmBl, p);
+            }
+        }
     }
     VELO_LAUNCH_CHECK();
     return VELO_OK;
