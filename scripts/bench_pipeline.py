@@ -35,7 +35,8 @@ def timed(name, fn):
 
 timed("normalize('both') [first use: H2D of S and U]", lambda: vlm.normalize("both", size=True, log=True))
 timed("normalize('both') again (resident)", lambda: vlm.normalize("both", size=True, log=True))
-timed("perform_PCA(n_components=25)", lambda: vlm.perform_PCA(n_components=25))
+timed("perform_PCA(n_components=25) [first call: cuSOLVER / cuBLAS fp64 initialisation]", lambda: vlm.perform_PCA(n_components=25))
+timed("perform_PCA(n_components=25) again", lambda: vlm.perform_PCA(n_components=25))
 timed(f"knn_imputation(k={k}, n_pca_dims=20) [device kNN + K5 x2]", lambda: vlm.knn_imputation(k=k, n_pca_dims=20, n_jobs=8))
 timed("knn_imputation again", lambda: vlm.knn_imputation(k=k, n_pca_dims=20, n_jobs=8))
 timed("fit_gammas() default (weights + box-constrained fit) [first call]", lambda: vlm.fit_gammas())

@@ -365,9 +365,14 @@ class VelocytoLoom:
         connectivity = connectivity_with_diagonal(self.knn, diag)                        # analysis.py:1006-1009
         # connectivity_to_weights (analysis.py:1010, neighbors.py:385-390) on the CSR arrays: rows / rowsum.  SciPy's
         # `multiply` by a dense column returns COO and costs a second at 5e6 edges; the values are the same.
-        rowsum = np.add.reduceat(connectivity.data, connectivity.indptr[:-1])
-        self.knn_smoothing_w = sparse.csr_matrix((connectivity.data / np.repeat(rowsum, np.diff(connectivity.indptr)),
-                                                  connectivity.indices, connectivity.indptr), shape=connectivity.shape)
+        n_rows, nnz = connectivity.shape[0], connectivity.indptr[-1]
+        if n_rows and nnz % n_rows == 0 and (np.diff(connectivity.indptr) == nnz // n_rows).all():
+            blk = connectivity.data.reshape(n_rows, nnz // n_rows)                       # regular graph: (n, k + 1) blocks
+            wdata = (blk / blk.sum(1, keepdims=True)).ravel()
+        else:
+            rowsum = np.add.reduceat(connectivity.data, connectivity.indptr[:-1])
+            wdata = connectivity.data / np.repeat(rowsum, np.diff(connectivity.indptr))
+        self.knn_smoothing_w = sparse.csr_matrix((wdata, connectivity.indices, connectivity.indptr), shape=connectivity.shape)
         self._smooth(maximum, size_norm)
 
     def knn_imputation_precomputed(self, knn_smoothing_w, maximum: bool = False) -> None:
@@ -562,7 +567,6 @@ class VelocytoLoom:
         float64 matrix when it fits comfortably (cells <= ``dense_limit``, default 20000) and is always
         available in compact form as ``corrcoef_compact`` / ``neigh_ixs`` (cells x m)."""
         import torch
-        from sklearn.neighbors import NearestNeighbors
         from . import device as dev
         dense_limit = kwargs.pop("dense_limit", 20000)
         # "reference" (default): the reference's NumPy / numba random streams on the host -- bit-equal sampling_ixs and
@@ -647,6 +651,7 @@ class VelocytoLoom:
         elif n_neighbors + 1 <= dev.KNN_MAX_K:                                           # analysis.py:1547-1549, on the device
             self.embedding_knn = knn_graph_device(np.asarray(embedding), n_neighbors + 1, "connectivity")
         else:
+            from sklearn.neighbors import NearestNeighbors       # only beyond the device kernel's k limit (1.4 s of import)
             nn = NearestNeighbors(n_neighbors=n_neighbors + 1, n_jobs=n_jobs)
             nn.fit(embedding)
             self.embedding_knn = nn.kneighbors_graph(mode="connectivity")
