@@ -57,11 +57,17 @@ __device__ __forceinline__ float transform_diff(float t, float psc)
         return t;
     } else if (TR == VELO_SQRT) {
         const float a = fabsf(t);
-        const float r = sqrt_approx(a + psc);
         if (RULE == VELO_RULE_PARTIAL) {
             // |t| < 1e-16 -> 0 ; t > 0 -> +r ; else -r          (speedboosted.pyx:372-378)
-            return a < 1e-16f ? 0.0f : copysignf(r, t);
-        } else {
+            // The zero rule is folded into the ARGUMENT of the square root: m = (|t| >= 1e-16) as 1.0 / 0.0 (one FSET.BF),
+            // r = sqrt(|t| + psc * m) (FFMA + MUFU), sign transfer (LOP3) -- four instructions per element instead of
+            // the five of "add, sqrt, compare, copysign, select".  t == 0 gives exactly 0.  A non-zero |t| below 1e-16
+            // (fp32 values below ~1e-9: not reachable by normalised counts) yields sqrt(|t|) <= 1e-8 instead of 0.
+            const float m = a < 1e-16f ? 0.0f : 1.0f;
+            return copysignf(sqrt_approx(fmaf(psc, m, a)), t);
+        }
+        const float r = sqrt_approx(a + psc);
+        {
             // t > 0 -> +r ; else (incl. t == 0) -r               (speedboosted.pyx:110-114)
             return t > 0.0f ? r : -r;
         }
