@@ -316,32 +316,56 @@ __global__ void __launch_bounds__(K1Cfg<EXACT>::threads, 1) k_coldeltacor(const 
                     Acc4 aA, aB;
                     aA.s1[0] = aA.s2[0] = aA.s3[0] = make_float2(0.0f, 0.0f);
                     aB.s1[0] = aB.s2[0] = aB.s3[0] = make_float2(0.0f, 0.0f);
-                    for (int base = 0; base < nq; base += 64) {           // warp-uniform trip count
+                    // One trip = 64 float4 per row (two per lane and row).  The trips are split into a STEADY loop
+                    // (every trip but the last complete one: the next group is a complete group of the same rows, so
+                    // the loop carries no bounds logic at all -- round 2 counted ~2 control / address instructions
+                    // per element in the single generic loop, a fifth of the issue slots), the last complete trip
+                    // (whose prefetch is the ragged remainder or the first group of the warp's next rows) and the
+                    // ragged remainder.
+                    auto trip = [&](int base, bool prefetch_same_rows) {
                         const int j = base + lane;
                         const float *loA = EXACT ? reinterpret_cast<const float *>(rowA + j) + lo_delta : nullptr;
                         const float *loB = EXACT ? reinterpret_cast<const float *>(rowB + j) + lo_delta : nullptr;
                         const float *lo_c = EXACT ? lo_c_row + 4 * j : nullptr;
-                        if (base + 64 <= nq) {
-                            const float4 ec0 = s_e4[j], ec1 = s_e4[j + 32];
-                            const Diff4 dA0 = diff4<EXACT>(cur[0], ec0), dA1 = diff4<EXACT>(cur[1], ec1);
-                            const Diff4 dB0 = diff4<EXACT>(cur[2], ec0), dB1 = diff4<EXACT>(cur[3], ec1);
-                            if (base + 64 < nq) load_pair(rowA, rowB, base + 64);
-                            else if (rowA2) load_pair(rowA2, rowB2, 0);
-                            const float4 b0 = s_b4[j], b1 = s_b4[j + 32];
-                            accumulate_diff<TR, RULE, EXACT>(aA, dA0, b0, p.psc, loA, lo_c);
-                            accumulate_diff<TR, RULE, EXACT>(aB, dB0, b0, p.psc, loB, lo_c);
-                            accumulate_diff<TR, RULE, EXACT>(aA, dA1, b1, p.psc, loA + 128, lo_c + 128);
-                            accumulate_diff<TR, RULE, EXACT>(aB, dB1, b1, p.psc, loB + 128, lo_c + 128);
-                        } else {                                          // ragged last group of the row
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                if (j + 32 * k < nq) {
-                                    const float4 ec = s_e4[j + 32 * k], bb = s_b4[j + 32 * k];
-                                    accumulate4<TR, RULE, EXACT>(aA, cur[k], ec, bb, p.psc, loA + 128 * k, lo_c + 128 * k);
-                                    accumulate4<TR, RULE, EXACT>(aB, cur[2 + k], ec, bb, p.psc, loB + 128 * k, lo_c + 128 * k);
-                                }
-                            if (rowA2) load_pair(rowA2, rowB2, 0);         // base + 64 >= nq here
+                        const float4 ec0 = s_e4[j], ec1 = s_e4[j + 32];
+                        const Diff4 dA0 = diff4<EXACT>(cur[0], ec0), dA1 = diff4<EXACT>(cur[1], ec1);
+                        const Diff4 dB0 = diff4<EXACT>(cur[2], ec0), dB1 = diff4<EXACT>(cur[3], ec1);
+                        if (prefetch_same_rows) {                      // complete group: no predicates
+                            cur[0] = ldg_stream_f4(rowA + j + 64);
+                            cur[1] = ldg_stream_f4(rowA + j + 96);
+                            cur[2] = ldg_stream_f4(rowB + j + 64);
+                            cur[3] = ldg_stream_f4(rowB + j + 96);
+                        } else if (base + 64 < nq) {
+                            load_pair(rowA, rowB, base + 64);
+                        } else if (rowA2) {
+                            load_pair(rowA2, rowB2, 0);
                         }
+                        const float4 b0 = s_b4[j], b1 = s_b4[j + 32];
+                        accumulate_diff<TR, RULE, EXACT>(aA, dA0, b0, p.psc, loA, lo_c);
+                        accumulate_diff<TR, RULE, EXACT>(aB, dB0, b0, p.psc, loB, lo_c);
+                        accumulate_diff<TR, RULE, EXACT>(aA, dA1, b1, p.psc, loA + 128, lo_c + 128);
+                        accumulate_diff<TR, RULE, EXACT>(aB, dB1, b1, p.psc, loB + 128, lo_c + 128);
+                    };
+                    const int full = nq >> 6;                           // complete trips (warp-uniform)
+                    int base = 0;
+                    for (int tr = 0; tr + 1 < full; ++tr, base += 64) trip(base, true);
+                    if (full > 0) {
+                        trip(base, false);
+                        base += 64;
+                    }
+                    if (base < nq) {                                    // ragged last group of the row
+                        const int j = base + lane;
+                        const float *loA = EXACT ? reinterpret_cast<const float *>(rowA + j) + lo_delta : nullptr;
+                        const float *loB = EXACT ? reinterpret_cast<const float *>(rowB + j) + lo_delta : nullptr;
+                        const float *lo_c = EXACT ? lo_c_row + 4 * j : nullptr;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            if (j + 32 * k < nq) {
+                                const float4 ec = s_e4[j + 32 * k], bb = s_b4[j + 32 * k];
+                                accumulate4<TR, RULE, EXACT>(aA, cur[k], ec, bb, p.psc, loA + 128 * k, lo_c + 128 * k);
+                                accumulate4<TR, RULE, EXACT>(aB, cur[2 + k], ec, bb, p.psc, loB + 128 * k, lo_c + 128 * k);
+                            }
+                        if (rowA2) load_pair(rowA2, rowB2, 0);
                     }
                     finish_row(nA, aA);
                     if (hasB) finish_row(nB, aB);
