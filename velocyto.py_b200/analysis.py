@@ -11,14 +11,18 @@ fp32 (``device.CellMajor``).  The big ``(genes, cells)`` attributes (``Sx_sz``, 
 ...) are materialised as float64 NumPy arrays only when they are read, so ``to_hdf5``-style consumers
 and plotting code keep working while a 100k-cell pipeline never round-trips through the host.
 
-What stays on the host, as in the reference: the kNN searches (scikit-learn, analysis.py:1005,1547 --
-SURVEY.md 8f "next"), the neighbour sampler and the randomised control (NumPy / numba RNG streams must
-match the reference's, analysis.py:1552-1566, 2407-2420), and the O(nnz) graph bookkeeping.
+What stays on the host, as in the reference: the neighbour sampler and the randomised control BY DEFAULT (NumPy /
+numba RNG streams must match the reference's for identical ``sampling_ixs`` / ``delta_S_rndm``, analysis.py:1552-1566,
+2407-2420 -- the sampler runs as a C++ restatement of the NumPy stream, ``csrc/host_sampler.cpp``;
+``random_backend="device"`` moves both to the GPU with their own streams), BalancedKNN's greedy pass (sequential by
+construction) and the O(nnz) graph bookkeeping.  The kNN searches run on the device (exact, brute force).
 
-The size/log normalisation family (``normalize``, analysis.py:535-676) also runs on the device (SURVEY.md 8f "next").
-Out of scope: loom I/O, filtering, PCA/TSNE, plotting, Markov.
-Objects are therefore built from arrays: ``VelocytoLoom(S=..., U=...)``, then ``normalize(...)`` and the caller sets
-``pcs``/``ts`` exactly as the reference's ``perform_PCA`` / embedding methods would have.
+Also mirrored (SURVEY.md 8f "next" rows): ``normalize`` (analysis.py:535-676), ``perform_PCA`` (:678-702),
+``calculate_grid_arrows`` (:1735-1816), and sparse ingest -- ``VelocytoLoom(S=<scipy sparse>, U=...)`` /
+``VelocytoLoom.from_csr(...)`` keep the count layers sparse on the host and upload them as CSR by cell.
+Out of scope: loom / HDF5 file parsing, filtering, TSNE, plotting, Markov diffusion.
+The dense ``(cells, cells)`` results (``corrcoef``, ``transition_prob`` and their ``_random`` twins) are built lazily, the
+first time they are read, from the compact ``(cells, m)`` device results (``*_compact`` + ``neigh_ixs``).
 """
 from __future__ import annotations
 

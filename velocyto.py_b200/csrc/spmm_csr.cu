@@ -35,12 +35,21 @@ __global__ void __launch_bounds__(256) k_knn_smooth_csr(const int64_t *__restric
                                                         const float *__restrict__ s_values, float *__restrict__ out,
                                                         int64_t ld_out, int64_t g0, int64_t ng, int maximum)
 {
-    __shared__ long long acc[kTileGenes];
+    // 64-bit fixed-point accumulators kept as two 32-bit halves: a 64-bit shared-memory atomicAdd compiles to a
+    // compare-and-swap spin loop (ATOMS.CAST.SPIN.64), two 32-bit adds are native (ATOMS.ADD).  The low half wraps
+    // mod 2^32; the add that causes a wrap sees it in the value it gets back and forwards the carry to the high half.
+    // Integer additions commute, every carry is counted exactly once: the pair is the exact 64-bit sum whatever the
+    // order in which warps arrive -- bit-reproducible, like the single 64-bit accumulator it replaces.
+    __shared__ unsigned int acc_lo[kTileGenes];
+    __shared__ unsigned int acc_hi[kTileGenes];
     const int64_t c = blockIdx.x;
     const int64_t t0 = static_cast<int64_t>(blockIdx.y) * kTileGenes;          // tile start within the slab
     const int tile = static_cast<int>(min(static_cast<int64_t>(kTileGenes), ng - t0));
     const int32_t gene_lo = static_cast<int32_t>(g0 + t0), gene_hi = gene_lo + tile;
-    for (int i = threadIdx.x; i < tile; i += blockDim.x) acc[i] = 0;
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) {
+        acc_lo[i] = 0u;
+        acc_hi[i] = 0u;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t p0 = w_indptr[c], p1 = w_indptr[c + 1];
@@ -62,7 +71,11 @@ __global__ void __launch_bounds__(256) k_knn_smooth_csr(const int64_t *__restric
     auto scatter = [&](int64_t a, int64_t b, double w) {
         for (int64_t q = a + lane; q < b; q += 32) {
             const long long v = __double2ll_rn(w * static_cast<double>(s_values[q]));
-            atomicAdd(reinterpret_cast<unsigned long long *>(&acc[s_genes[q] - gene_lo]), static_cast<unsigned long long>(v));
+            const unsigned int vlo = static_cast<unsigned int>(v), vhi = static_cast<unsigned int>(v >> 32);
+            const int g = s_genes[q] - gene_lo;
+            const unsigned int old = atomicAdd(&acc_lo[g], vlo);
+            const unsigned int carry = (old + vlo) < old ? 1u : 0u;
+            if (vhi + carry) atomicAdd(&acc_hi[g], vhi + carry);
         }
     };
     for (int64_t p = p0 + warp; p < p1; p += 2 * nwarps) {
@@ -80,7 +93,8 @@ __global__ void __launch_bounds__(256) k_knn_smooth_csr(const int64_t *__restric
     __syncthreads();
     float *orow = out + c * ld_out + t0;
     for (int i = threadIdx.x; i < tile; i += blockDim.x)
-        orow[i] = static_cast<float>(static_cast<double>(acc[i]) * (1.0 / kFixScale));
+        orow[i] = static_cast<float>(static_cast<double>(static_cast<long long>((static_cast<unsigned long long>(acc_hi[i]) << 32) |
+                                                                                 acc_lo[i])) * (1.0 / kFixScale));
     if (maximum) {                                                               // np.maximum(S, Sx): own row, sparse
         __syncthreads();
         const int64_t r0 = s_indptr[c], r1 = s_indptr[c + 1];
