@@ -189,10 +189,10 @@ def main():
     barrier()
     with T("k5_csr_S"):
         Sx2 = smooth(S_csr)
-    with T("k5_csr_U"):
-        Ux = smooth(U_csr)
     deterministic = bool(torch.equal(Sx.t, Sx2.t))
     del Sx2
+    with T("k5_csr_U"):
+        Ux = smooth(U_csr)
     # column sums: sum_c Sx[c, g] == sum_j (sum_c w[c, j]) * S[j, g]   (size-independent property of the SpMM)
     win = torch.zeros(C, dtype=torch.float64, device=device).index_add_(0, w_ix.to(torch.int64), w_wt.double())
     rows = torch.repeat_interleave(torch.arange(C, device=device), S_csr[0][1:] - S_csr[0][:-1])
