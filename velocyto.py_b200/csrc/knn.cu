@@ -255,15 +255,14 @@ static int knn_launch(const double *X, const double *Q, int64_t C, int D, int k,
     if (rc) return rc;
     int P = 64;
     while (P < k + (k >> 3) + 32) P <<= 1;                 // room for fp32-key ties at the threshold
-    // query tile: 8 (D <= 32) or 4 (D <= 64) queries share one sweep over the points; the per-CTA key scratch grows with
-    // the tile (QT x C x 4 bytes), so the larger tile is only taken while that stays below ~16 GB in total
-    int QT = 1;
-    if (D <= 64 && nq >= 4) QT = 4;
-    if (D <= 32 && nq >= 8 && static_cast<double>(C) * 4 * 8 * dp.sm_count * 4 < 16e9) QT = 8;
+    // query tile: 4 queries share one sweep over the points when their coordinates fit next to the candidate buffers
+    // (a tile of 8 was measured and is SLOWER: 3.96 s vs 3.77 s at 500k x 20-D, 154 vs 96 ms at 100k x 2-D with k = 3000 --
+    // the per-CTA key scratch doubles and the select passes, not the sweep, dominate by then)
+    const int QT = (D <= 64 && nq >= 4) ? 4 : 1;
     const size_t smem = static_cast<size_t>(P) * 12 + static_cast<size_t>(D) * 8 * QT + 16;
     VELO_REQUIRE(smem + 2048 <= static_cast<size_t>(dp.smem_optin), "knn: k = %d too large for shared memory (max ~14000)", k);
     cudaStream_t st = as_stream(stream);
-    auto kern = QT == 8 ? k_knn_bruteforce<8> : (QT == 4 ? k_knn_bruteforce<4> : k_knn_bruteforce<1>);
+    auto kern = QT == 4 ? k_knn_bruteforce<4> : k_knn_bruteforce<1>;
     VELO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 1;
     VELO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem));
