@@ -87,10 +87,9 @@ __global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
             const int shift = 24 - 8 * pass;
             for (int b = tid; b < 256; b += nt) hist[b] = 0;
             __syncthreads();
-            for (int64_t j0 = tid - (tid & 31); j0 < p.C; j0 += nt) {            // warp-uniform trip count
-                const int64_t j = j0 + (tid & 31);
-                const uint32_t u = j < p.C ? keys[j] : 0u;
-                hist_add_aggregated(hist, (u >> shift) & 255u, j < p.C && (u & mask) == prefix);
+            for (int64_t j = tid; j < p.C; j += nt) {
+                const uint32_t u = keys[j];
+                if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
             }
             __syncthreads();
             if (tid == 0) {
@@ -145,11 +144,9 @@ __global__ void __launch_bounds__(512) k_knn_bruteforce(const KnnParams p)
                 const int shift = 24 - 8 * pass;
                 for (int b = tid; b < 256; b += nt) hist[b] = 0;
                 __syncthreads();
-                for (int64_t j0 = tid - (tid & 31); j0 < p.C; j0 += nt) {
-                    const int64_t j = j0 + (tid & 31);
-                    const bool on = j < p.C && keys[j] == prefix && (static_cast<uint32_t>(j) & imask) == ipre;
-                    hist_add_aggregated(hist, (static_cast<uint32_t>(j) >> shift) & 255u, on);
-                }
+                for (int64_t j = tid; j < p.C; j += nt)
+                    if (keys[j] == prefix && (static_cast<uint32_t>(j) & imask) == ipre)
+                        atomicAdd(&hist[(static_cast<uint32_t>(j) >> shift) & 255u], 1u);
                 __syncthreads();
                 if (tid == 0) {
                     int64_t cum = 0;

@@ -49,11 +49,10 @@ __device__ void block_select_pair(const float *__restrict__ row, int64_t n, int6
         const int shift = 24 - 8 * pass;
         for (int b = tid; b < 256; b += nt) hist[b] = 0;
         __syncthreads();
-        for (int64_t i0 = tid - (tid & 31); i0 < n; i0 += nt) {                  // warp-uniform trip count
-            const int64_t i = i0 + (tid & 31);
-            const bool in = i < n && pred(i);
-            const uint32_t u = in ? f2key(row[i]) : 0u;
-            hist_add_aggregated(hist, (u >> shift) & 255u, in && (u & mask) == prefix);
+        for (int64_t i = tid; i < n; i += nt) {
+            if (!pred(i)) continue;
+            const uint32_t u = f2key(row[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         }
         __syncthreads();
         if (tid == 0) {

@@ -138,19 +138,6 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// Histogram increment with warp-level aggregation: lanes that hit the same bin elect one of them to add their count.
-// Radix-select histograms over keys of real data are extremely skewed (all distances of a query, or all values of a
-// gene, share their leading byte): plain shared-memory atomics then serialise 32 ways per warp instruction.
-// EVERY lane of the warp must call this (converged); lanes with nothing to add pass active = false.
-__device__ __forceinline__ void hist_add_aggregated(unsigned int *hist, unsigned int bin, bool active)
-{
-    const unsigned int act = __ballot_sync(0xffffffffu, active);
-    if (active) {
-        const unsigned int peers = __match_any_sync(act, bin);
-        if ((threadIdx.x & 31) == static_cast<unsigned int>(__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
-    }
-}
-
 // Packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2 issue two fp32 operations per instruction slot)
 __device__ __forceinline__ float2 sub2(float2 a, float2 b)
 {
