@@ -67,5 +67,27 @@ flag2 = torch.tensor([1 if ok2 else 0], device="cuda")
 dist.all_reduce(flag2, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"gene-sharded smooth+fit+chain -> all-to-all -> cell-sharded corr == single-GPU: {bool(flag2.item())}")
+
+# ---- stage 3: the host-buffer front (CellShardedHostTransitionProb): sub-block upload pipelined with the all-gathers,
+#      raw float64 data (residual matrix + EXACT kernel), blocks handed over as strided views of the full host matrices ----
+from velocyto_b200.sharding import CellShardedHostTransitionProb
+G3, C3, m3 = 257, 4 * 4096 * world + 37, 33                  # b >= 4096: the 4-sub-block path; uneven last block
+rng3 = np.random.default_rng(5)
+e3 = rng3.gamma(2.0, 1.0, (G3, C3))
+e3[rng3.uniform(size=e3.shape) < 0.3] = 0
+d3 = np.sqrt(np.abs(rng3.normal(size=(G3, C3))) + psc) * np.sign(rng3.normal(size=(G3, C3)))
+ix3 = ((np.arange(C3)[:, None] + 1 + rng3.integers(0, C3 - 1, (C3, m3))) % C3).astype(np.int64)
+host = CellShardedHostTransitionProb(G3, C3, "sqrt", psc, 0.05)
+out3 = np.empty((host.nc, m3), dtype=np.float32)
+host.run(e3[:, host.c0:host.c0 + host.nc], d3[:, host.c0:host.c0 + host.nc], ix3[host.c0:host.c0 + host.nc], out3)
+host.run(e3[:, host.c0:host.c0 + host.nc], d3[:, host.c0:host.c0 + host.nc], ix3[host.c0:host.c0 + host.nc], out3)   # buffers reused
+e3d, d3d = dev.CellMajor.from_gene_major(e3, residual=True), dev.CellMajor.from_gene_major(d3)
+ix3d = dev.indices_to_device(ix3, C3)
+ref3 = dev.transition_prob(dev.coldeltacor(e3d, d3d, ix3d, "sqrt", psc), ix3d, 0.05)
+ok3 = e3d.lo is not None and torch.equal(torch.from_numpy(out3).cuda(), ref3[host.c0:host.c0 + host.nc])
+flag3 = torch.tensor([1 if ok3 else 0], device="cuda")
+dist.all_reduce(flag3, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"host-buffer sharded front (sub-block upload + all-gather pipeline, EXACT path) == single-GPU: {bool(flag3.item())}")
 dist.destroy_process_group()
-sys.exit(0 if (flag.item() and flag2.item()) else 1)
+sys.exit(0 if (flag.item() and flag2.item() and flag3.item()) else 1)

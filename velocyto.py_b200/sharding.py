@@ -156,23 +156,44 @@ class CellShardedHostTransitionProb:
         if want_lo and self._lo_full is None:
             self._lo_full = torch.zeros((self.world * b, ld), dtype=torch.float32, device=device)
         stream = torch.cuda.current_stream().cuda_stream
-        mine = self._e_full[self.rank * b:(self.rank + 1) * b]
-        lo_mine = self._lo_full[self.rank * b:(self.rank + 1) * b] if want_lo else None
         import ctypes
-        nz = ctypes.c_int(0)
-        if nc:
-            _cabi.call("velo_upload_cellmajor", e_ptr, e_sz, G, nc, e_pitch, mine.data_ptr(),
-                       0 if lo_mine is None else lo_mine.data_ptr(), ctypes.addressof(nz) if want_lo else 0, ld, stream)
+        # The block goes up in SUB-BLOCKS of cells; the all-gather of sub-block s (NCCL's own stream, NVLink) runs while
+        # sub-block s + 1 is still crossing PCIe.  All ranks cut at the same local rows (multiples of sb inside the
+        # uniform block b), so the collectives line up; rows past a short last block are padding nobody indexes.
+        # The residual sub-blocks are gathered optimistically whenever the input CAN need them (their traffic hides
+        # under the upload); whether the kernel uses them is decided once, by one all-reduce of the per-rank flags.
+        S = 4 if (self.world > 1 and b >= 4 * 1024) else 1
+        sb = (b + S - 1) // S
+        nz_any, works = 0, []
+        for s0 in range(0, b, sb):
+            s1 = min(b, s0 + sb)
+            n_up = max(0, min(nc, s1) - s0)                       # rows of this sub-block that exist on this rank
+            lo_off = self.rank * b + s0
+            if n_up:
+                nz = ctypes.c_int(0)
+                _cabi.call("velo_upload_cellmajor", e_ptr + s0 * e_sz, e_sz, G, n_up, e_pitch,
+                           self._e_full[lo_off:].data_ptr(), self._lo_full[lo_off:].data_ptr() if want_lo else 0,
+                           ctypes.addressof(nz) if want_lo else 0, ld, stream)
+                nz_any |= nz.value
+            if self.world > 1:
+                if S == 1:
+                    mine = self._e_full[self.rank * b:(self.rank + 1) * b]
+                    dist.all_gather_into_tensor(self._e_full, mine, group=self.group)          # in place: slot `rank`
+                    if want_lo:
+                        dist.all_gather_into_tensor(self._lo_full, self._lo_full[self.rank * b:(self.rank + 1) * b],
+                                                    group=self.group)
+                else:
+                    for full in ((self._e_full, self._lo_full) if want_lo else (self._e_full,)):
+                        outs = [full[r * b + s0:r * b + s1] for r in range(self.world)]
+                        works.append(dist.all_gather(outs, full[lo_off:self.rank * b + s1], group=self.group, async_op=True))
+        for w in works:
+            w.wait()                                              # stream-level: the current stream waits for the gathers
         use_lo = False
         if want_lo:
-            flag = torch.tensor([nz.value], device=device, dtype=torch.int32)
+            flag = torch.tensor([nz_any], device=device, dtype=torch.int32)
             if self.world > 1:
                 dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
             use_lo = bool(flag.item())                      # any rank's block not fp32-representable
-        if self.world > 1:
-            dist.all_gather_into_tensor(self._e_full, mine, group=self.group)          # in place: mine IS slot `rank`
-            if use_lo:
-                dist.all_gather_into_tensor(self._lo_full, lo_mine, group=self.group)
         if nc:
             _cabi.call("velo_transition_prob_partial_sharded", _cabi.TRANSFORMS[self.transform], self._e_full.data_ptr(),
                        self._lo_full.data_ptr() if use_lo else 0, ld, stream, d_ptr, d_sz, d_pitch, ix_ptr, o_ptr,
