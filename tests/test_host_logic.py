@@ -435,3 +435,62 @@ def test_host_sampler_consumes_numpys_legacy_stream_bit_for_bit():
         assert np.array_equal(got, want), (C, W)
         assert np.array_equal(state_got[1], state_want[1]) and state_got[2] == state_want[2]
         assert np.random.random() == (np.random.set_state(state_want) or np.random.random())   # and the NEXT draw agrees
+
+
+def test_connectivity_fast_path_equals_general_path():
+    """Regular kNN graphs (k entries per row, what the searches return) take an (n, k)-block shortcut in
+    connectivity_with_diagonal; zero distances or self edges fall back to the per-edge path.  Both must equal
+    ``(knn > 0).astype(float)`` + ``setdiag(diag)`` (analysis.py:1006-1009)."""
+    import warnings
+    from velocyto_b200.analysis import connectivity_with_diagonal
+    rng = np.random.default_rng(0)
+    n, k = 300, 9
+    idx = np.stack([rng.choice(np.delete(np.arange(n), c), k, replace=False) for c in range(n)])
+    dat = rng.uniform(0.1, 1.0, (n, k))
+
+    def ref(knn, diag):
+        conn = (knn > 0).astype(float)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            conn.setdiag(diag)
+        return conn
+
+    regular = sparse.csr_matrix((dat.ravel(), idx.ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+    dat0 = dat.copy()
+    dat0[5, 2] = 0.0                                                   # a zero-distance edge: dropped by `knn > 0`
+    with_zero = sparse.csr_matrix((dat0.ravel(), idx.ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+    idx_self = idx.copy()
+    idx_self[7, 0] = 7                                                 # a self edge: overwritten by setdiag
+    with_self = sparse.csr_matrix((dat.ravel(), idx_self.ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+    ragged = sparse.csr_matrix(regular.toarray() * (rng.uniform(size=(n, n)) < 0.7))
+    for knn in (regular, with_zero, with_self, ragged):
+        for diag in (1, 8):
+            assert (connectivity_with_diagonal(knn, diag) != ref(knn, diag)).nnz == 0
+    fast = connectivity_with_diagonal(regular, 1)
+    assert np.array_equal(fast.indices.reshape(n, k + 1)[:, 0], np.arange(n))      # diagonal first, kNN order kept
+    assert np.array_equal(fast.indices.reshape(n, k + 1)[:, 1:], idx)
+
+
+def test_velocytoloom_accepts_sparse_layers_and_lazy_dense_attributes():
+    """Host-side behaviour that needs no GPU: sparse count layers are kept sparse (no dense float64 copy), the
+    by-cell triplet constructor builds the same object, and the dense (cells x cells) result attributes are lazy
+    descriptors with ordinary set / get / delete semantics."""
+    from velocyto_b200.analysis import VelocytoLoom
+    rng = np.random.default_rng(1)
+    S = rng.poisson(0.3, (40, 25)).astype(np.float64)
+    U = rng.poisson(0.2, (40, 25)).astype(np.float64)
+    dense = VelocytoLoom(S=S, U=U)
+    sp = VelocytoLoom(S=sparse.csr_matrix(S), U=sparse.coo_matrix(U))
+    assert sparse.issparse(sp.S) and sparse.issparse(sp.U) and sp.S.shape == (40, 25)
+    np.testing.assert_array_equal(sp.initial_cell_size, dense.initial_cell_size)
+    np.testing.assert_array_equal(sp.initial_Ucell_size, dense.initial_Ucell_size)
+    cs, cu = sparse.csc_matrix(S), sparse.csc_matrix(U)
+    tri = VelocytoLoom.from_csr((cs.data, cs.indices, cs.indptr), (cu.data, cu.indices, cu.indptr), n_genes=40)
+    assert (tri.S != sp.S).nnz == 0 and (tri.U != sp.U).nnz == 0
+    with pytest.raises(AttributeError):
+        dense.corrcoef                                                  # nothing computed yet
+    assert not hasattr(dense, "transition_prob")
+    dense.corrcoef = np.eye(3)                                          # a user assignment is kept as it is
+    assert np.array_equal(dense.corrcoef, np.eye(3))
+    del dense.corrcoef
+    assert not hasattr(dense, "corrcoef")
