@@ -6,6 +6,7 @@ import socket
 import sys
 
 import numpy as np
+from scipy import sparse
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -466,7 +467,10 @@ def test_connectivity_fast_path_equals_general_path():
     for knn in (regular, with_zero, with_self, ragged):
         for diag in (1, 8):
             assert (connectivity_with_diagonal(knn, diag) != ref(knn, diag)).nnz == 0
-    fast = connectivity_with_diagonal(regular, 1)
+    # (SciPy's `knn > 0` in ref() canonicalised `regular` in place -- the reference does the same to self.knn -- so the
+    # order check uses a fresh matrix)
+    fresh = sparse.csr_matrix((dat.ravel(), idx.ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+    fast = connectivity_with_diagonal(fresh, 1)
     assert np.array_equal(fast.indices.reshape(n, k + 1)[:, 0], np.arange(n))      # diagonal first, kNN order kept
     assert np.array_equal(fast.indices.reshape(n, k + 1)[:, 1:], idx)
 
