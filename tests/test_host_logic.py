@@ -498,3 +498,38 @@ def test_velocytoloom_accepts_sparse_layers_and_lazy_dense_attributes():
     assert np.array_equal(dense.corrcoef, np.eye(3))
     del dense.corrcoef
     assert not hasattr(dense, "corrcoef")
+
+
+def test_smoothing_weights_from_knn_equals_reference_sequence():
+    """knn_imputation's graph preparation in one step (smoothing_weights_from_knn) == the reference's sequence
+    ``(knn > 0).astype(float)``, ``setdiag(diag)``, ``connectivity_to_weights`` (analysis.py:1006-1010) -- closed form for
+    regular kNN graphs, general path for zero distances, self edges and ragged rows."""
+    import warnings
+    from velocyto_b200.analysis import smoothing_weights_from_knn
+    from velocyto_b200.neighbors import connectivity_to_weights
+    rng = np.random.default_rng(3)
+    n, k = 180, 11
+    idx = np.stack([rng.choice(np.delete(np.arange(n), c), k, replace=False) for c in range(n)])
+    dist = rng.uniform(0.1, 1.0, (n, k))
+    mk = lambda d, i: sparse.csr_matrix((d.ravel(), i.astype(np.int32).ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+
+    def ref(knn, diag):
+        conn = (knn > 0).astype(float)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            conn.setdiag(diag)
+        return sparse.csr_matrix(connectivity_to_weights(conn))
+
+    d0 = dist.copy()
+    d0[3, 2] = 0.0
+    i_self = idx.copy()
+    i_self[9, 0] = 9
+    ragged = sparse.csr_matrix(mk(dist, idx).toarray() * (rng.uniform(size=(n, n)) < 0.6))
+    for knn_fn in (lambda: mk(dist, idx), lambda: mk(d0, idx), lambda: mk(dist, i_self), lambda: ragged.copy()):
+        for diag in (1, 8, 0.5):
+            got, want = smoothing_weights_from_knn(knn_fn(), diag), ref(knn_fn(), diag)
+            assert abs(got - want).max() < 1e-15
+            np.testing.assert_allclose(np.asarray(got.sum(1)).ravel(), 1.0, rtol=1e-13)
+    w = smoothing_weights_from_knn(mk(dist, idx), 1)                     # regular graph: diagonal first, kNN order kept
+    assert np.array_equal(w.indices.reshape(n, k + 1)[:, 0], np.arange(n))
+    assert np.array_equal(w.indices.reshape(n, k + 1)[:, 1:], idx)
