@@ -269,3 +269,26 @@ def test_gemm_identity_and_fp16_pair_split_reproduce_linear_coldeltacor(oracle):
         errs[dtype] = np.abs(corr_from(P, Q) - want)[off].max()
     assert errs[torch.float16] < 5e-8, errs                                                      # (2)
     assert errs[torch.bfloat16] > 2e-7, errs
+
+
+def test_config1_fit_gammas_reference_path_at_full_shape(oracle):
+    """BASELINE config 1 (1k cells x 2k genes, fit_gammas on the reference CPU path; plumbing, no GPU): the oracle's
+    restatement of the unweighted fits (estimation.py:173-188, 244-297: one SciPy nnls / leastsq call per gene) at the
+    full shape against the solver-independent closed forms SURVEY.md section 7 established -- nnls == max(0, Sxy / Sxx) to
+    float32 rounding, leastsq == OLS to ~1e-5 -- which are also what the device kernel K4 evaluates."""
+    rng = np.random.default_rng(1)
+    G, C = 2000, 1000
+    mu = rng.gamma(0.6, 2.0, G)
+    s = rng.gamma(2.0, 0.5, C)
+    gam = rng.uniform(0.05, 1.0, G)
+    S = rng.poisson(mu[:, None] * s[None, :]).astype(np.float64) + rng.uniform(0, 0.5, (G, C))
+    U = rng.poisson(mu[:, None] * s[None, :] * gam[:, None]).astype(np.float64) + rng.uniform(0, 0.5, (G, C))
+    got = oracle.fit_slope(U, S)                                       # Y = U, X = S (analysis.py:1254-1256)
+    want = np.maximum(0.0, (S * U).sum(1) / (S * S).sum(1))
+    assert got.dtype == np.float32 and got.shape == (G,)
+    np.testing.assert_allclose(got, want, rtol=2e-7, atol=0)
+    g_o, q_o = oracle.fit_slope_offset(U, S)
+    xm, ym = S.mean(1, keepdims=True), U.mean(1, keepdims=True)
+    slope = ((S - xm) * (U - ym)).sum(1) / ((S - xm) ** 2).sum(1)
+    np.testing.assert_allclose(g_o, slope, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(q_o, (ym - slope[:, None] * xm).ravel(), rtol=2e-5, atol=2e-5)
