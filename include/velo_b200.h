@@ -119,7 +119,10 @@ int velo_host_sample_neighbors_numpy(uint32_t seed, int64_t n_cells, int W, cons
  * block of the reference's rows x cols matrix) -- to nc cell-major fp32 DEVICE rows dst_cm (row stride ld), in
  * gene-row chunks through PCIe with the transpose/convert on the device.  Pageable host memory is staged through
  * the library's pinned ring by several host threads.  dst_lo_cm != NULL also writes the fp32 residuals of fp64 data
- * and sets *lo_nonzero (host int) to 1 when any is non-zero (then the call synchronises `stream`). */
+ * and sets *lo_nonzero (host int) to 1 when any is non-zero (then the call synchronises `stream`).
+ * Otherwise the call is asynchronous on `stream`: a PAGE-LOCKED source is read by the copy engine until the work
+ * queued here completes (do not modify or free it before synchronising `stream`); a pageable source has been
+ * consumed when the call returns. */
 int velo_upload_cellmajor(const void *src_gc, int elem_bytes, int64_t rows, int64_t nc, int64_t src_cols,
                           float *dst_cm, float *dst_lo_cm, int *lo_nonzero, int64_t ld, velo_stream_t stream);
 /* velo_transition_prob_partial for the local cells of one rank, once the expression rows of ALL cells are resident on
